@@ -1,0 +1,157 @@
+/*
+ * pointops_b200.h -- C ABI of libpointops_b200.so, the B200 (sm_100a) replacement for the
+ * native half of the reference package `pointops` (JinfengX/PointCloudPDF, libs/pointops).
+ *
+ * Boundary.  The reference binds 16 pybind functions `*_cuda(sizes..., at::Tensor...)`
+ * (libs/pointops/src/pointops_api.cpp:15-32); each one only unwraps data pointers and calls an
+ * `extern "C"` launcher taking raw device pointers and int sizes.  This header declares the
+ * drop-in for those launchers: the same argument meaning and order, with
+ *   - sizes widened to int64_t (the reference's int products overflow above 2^31 elements),
+ *   - a trailing cudaStream_t (the reference launches on the legacy default stream),
+ *   - an int return: 0 on success, a cudaError_t from the launch, or a POB_ERR_* code;
+ *   - where a kernel needs scratch, a caller-owned workspace with a *_workspace_bytes query.
+ * No entry point allocates, frees, synchronises or reads device data on the host, so all of
+ * them are re-entrant, stream-ordered and CUDA-graph capturable.  All pointers are device
+ * pointers unless stated otherwise.  Tensors are dense row-major, f32 / i32 as in the reference.
+ *
+ * Batched-by-offset convention (libs/pointops/functions/query.py:9-24): a batch is the
+ * concatenation of scenes; `offset[b]` holds cumulative end rows.  Every neighbour search is
+ * restricted to the query's own scene.
+ */
+#ifndef POINTOPS_B200_H
+#define POINTOPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define POB_ERR_BAD_ARG 10001      /* null pointer / negative size / unsupported value */
+#define POB_ERR_WORKSPACE 10002    /* workspace smaller than *_workspace_bytes() */
+#define POB_ERR_UNSUPPORTED 10003
+
+/* ABI version; bumped on any signature change. */
+int pob_version(void);
+/* Human-readable text for a return code (cudaGetErrorString for CUDA codes). Host pointer. */
+const char* pob_error_string(int code);
+
+/* ------------------------------------------------------------------ kNN query ----------
+ * Replaces knn_query_cuda_launcher(m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2)
+ * (src/knn_query/knn_query_cuda_kernel.h:13; kernel knn_query_cuda_kernel.cu:60-104).
+ * idx (m, nsample) i32: the nsample nearest rows of the query's scene by the key (d2, idx),
+ * ascending; tail filled with -1 / 1e10 when the scene holds fewer points.  d2 is the f32 chain
+ * fma(dz,dz, fma(dx,dx, dy*dy)), what the reference binary executes.  dist receives d2
+ * (take_sqrt = 0, like the reference kernel) or sqrt(d2) (take_sqrt = 1, what
+ * functions/query.py:24 hands to callers); may be NULL.  nsample <= 256.
+ * Extra arguments vs the reference: n (rows of xyz) and b (scenes) size the search grid.      */
+size_t pob_knn_grid_workspace_bytes(int64_t n, int b, float cell_pts);
+int pob_knn_grid_build(int64_t n, int b, const float* xyz, const int* offset, float cell_pts,
+                       void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* Query a built grid (reusable for any new_xyz / nsample against the same xyz, offset).
+ * weight (m, nsample), optional: fused inverse-distance weights of
+ * functions/interpolation.py:15-17, w = r / sum(r), r = 1 / (sqrt(d2) + 1e-8).               */
+int pob_knn_grid_query(int64_t m, int nsample, int64_t n, int b, const float* xyz, const float* new_xyz,
+                       const int* new_offset, float cell_pts, const void* workspace, int* idx, float* dist,
+                       float* weight, int take_sqrt, cudaStream_t stream);
+/* Build + query in one call, cell_pts = 2; workspace >= pob_knn_grid_workspace_bytes(n, b, 2). */
+int pob_knn_query(int64_t m, int nsample, int64_t n, int b, const float* xyz, const float* new_xyz,
+                  const int* offset, const int* new_offset, int* idx, float* dist, int take_sqrt,
+                  void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* Exhaustive scan with the same key and arithmetic (O(m * n_scene)); workspace >= 64 * b bytes. */
+int pob_knn_query_bruteforce(int64_t m, int nsample, int b, const float* xyz, const float* new_xyz,
+                             const int* offset, const int* new_offset, int* idx, float* dist, int take_sqrt,
+                             void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ------------------------------------------------------- farthest point sampling -------
+ * Replaces farthest_point_sampling_cuda_launcher(b, n, xyz, offset, new_offset, tmp, idx)
+ * (src/sampling/sampling_cuda_kernel.h:13; kernel sampling_cuda_kernel.cu:15-129).
+ * n_max = size of the largest scene (the reference's `n`); an over-estimate is allowed, an
+ * under-estimate is not.  idx (new_offset[b-1]) i32 receives GLOBAL row indices, scene-major;
+ * first sample of a scene is its first row; ties go to the lowest index.  tmp (n f32) needs no
+ * initialisation and is only used when a scene exceeds the register-resident capacity
+ * (131072 points); it may be NULL below that.  cluster_hint: 0 = auto, or 1/2/4/8/16 CTAs per
+ * scene.  A scene requesting 0 samples writes nothing (reference quirk C5 not reproduced).      */
+int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, const int* offset,
+                                const int* new_offset, float* tmp, int* idx, int cluster_hint,
+                                cudaStream_t stream);
+
+/* --------------------------------------------------------- grouping (pointops.grouping2) --
+ * grouping_{forward,backward}_cuda_launcher (src/grouping/grouping_cuda_kernel.h:14-15).
+ * forward: output[m,s,:] = input[idx[m,s],:].  backward: grad_input[idx[m,s],:] += grad_output
+ * (grad_input must be zeroed by the caller, as functions/grouping.py:31 does).  idx >= 0.       */
+int pob_grouping_forward(int64_t m, int nsample, int c, const float* input, const int* idx, float* output,
+                         cudaStream_t stream);
+int pob_grouping_backward(int64_t m, int nsample, int c, const float* grad_output, const int* idx,
+                          float* grad_input, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------ subtraction ----
+ * subtraction_{forward,backward}_cuda_launcher (src/subtraction/subtraction_cuda_kernel.h:14-15).
+ * forward: output[n,s,:] = input1[n,:] - input2[idx[n,s],:].
+ * backward: grad_input1[n,:] = sum_s grad_output[n,s,:] (overwritten, no zeroing needed);
+ *           grad_input2[idx[n,s],:] -= grad_output[n,s,:] (accumulated; caller zeroes).         */
+int pob_subtraction_forward(int64_t n, int nsample, int c, const float* input1, const float* input2,
+                            const int* idx, float* output, cudaStream_t stream);
+int pob_subtraction_backward(int64_t n, int nsample, int c, const int* idx, const float* grad_output,
+                             float* grad_input1, float* grad_input2, cudaStream_t stream);
+
+/* ------------------------------------------------- vector-attention aggregation ----------
+ * aggregation_{forward,backward}_cuda_launcher (src/aggregation/aggregation_cuda_kernel.h:14-15).
+ * forward: output[n,c] = sum_s (input[idx[n,s],c] + position[n,s,c]) * weight[n,s,c % w_c]
+ *          (output overwritten; the reference accumulates into a zeroed buffer).
+ * backward: grad_input[idx[n,s],c] += g*w (accumulated; caller zeroes); grad_position = g*w and
+ *           grad_weight[n,s,j] = sum_{c % w_c == j} g * (input + position) (both overwritten).  */
+int pob_aggregation_forward(int64_t n, int nsample, int c, int w_c, const float* input, const float* position,
+                            const float* weight, const int* idx, float* output, cudaStream_t stream);
+int pob_aggregation_backward(int64_t n, int nsample, int c, int w_c, const float* input, const float* position,
+                             const float* weight, const int* idx, const float* grad_output, float* grad_input,
+                             float* grad_position, float* grad_weight, cudaStream_t stream);
+
+/* ------------------------------------------------------- three-NN interpolation ----------
+ * interpolation_{forward,backward}_cuda_launcher (src/interpolation/interpolation_cuda_kernel.h:14-15).
+ * forward: output[n,c] = sum_{i<k} input[idx[n,i],c] * weight[n,i] (overwritten).
+ * backward: grad_input[idx[n,i],c] += grad_output[n,c] * weight[n,i] (accumulated).             */
+int pob_interpolation_forward(int64_t n, int c, int k, const float* input, const int* idx, const float* weight,
+                              float* output, cudaStream_t stream);
+int pob_interpolation_backward(int64_t n, int c, int k, const float* grad_output, const int* idx,
+                               const float* weight, float* grad_input, cudaStream_t stream);
+
+/* ------------------------------------- fused grouping-with-xyz (additive entry point) ------
+ * One kernel for pointops.grouping (functions/grouping.py:36-60, pure torch there: 2 cats, 2
+ * gathers, mask, einsum, cat).  output (m, nsample, 3 + c) f32 when with_xyz else (m, nsample, c):
+ *   [ (xyz[idx] - new_xyz[m]) , feat[idx] ]  with all-zero rows where idx < 0.
+ * feat_dtype: 0 = f32, 1 = f16, 2 = bf16 (autocast); output is always f32 (torch promotion).
+ * backward: grad_feat[idx[m,s],:] += grad_output[m,s,(3 if with_xyz):] for idx >= 0 (f32,
+ * accumulated; caller zeroes).                                                                  */
+int pob_group_xyz_forward(int64_t m, int nsample, int c, int with_xyz, const void* feat, int feat_dtype,
+                          const float* xyz, const float* new_xyz, const int* idx, float* output,
+                          cudaStream_t stream);
+int pob_group_xyz_backward(int64_t m, int nsample, int c, int with_xyz, const float* grad_output, const int* idx,
+                           float* grad_feat, cudaStream_t stream);
+
+/* ------------------------------------------ fused open-set scoring (additive entry point) --
+ * One pass over logits (n, K) [+ conf (n)] replacing
+ *   MaxProbability msp / ml  (pointcept/recognizers/max_probability/max_probability_v1m1_base.py:17-29),
+ *   PointPdfV1 score         (pointcept/recognizers/ours/pointpdf_v1m1_base.py:106-113),
+ *   the scoring prefix of PointPdfV1.pseudo_labeling (pointpdf_v1m1_base.py:199-222).
+ * Per point (each pointer optional): msp_score = -max log_softmax, ml_score = -max logit,
+ * pdf_score = softmax(cat[logits, conf])[K] (needs conf), msp_prob = max softmax, max_logit,
+ * pred = argmax (first maximum), ml_norm = (max_logit - min_s) / (max_s - min_s + 1e-6).
+ * Per scene, scene_out (b, 8) f32: msp mean, msp std (unbiased), msp stop = mean - beta*std,
+ * then the same three for ml_norm, then min_s, max_s of the max logit.  Scene outputs need
+ * offset, b and a workspace of pob_score_workspace_bytes(b).                                    */
+size_t pob_score_workspace_bytes(int b);
+int pob_score_fused(int64_t n, int K, int b, const float* logits, const float* conf, const int* offset, float beta,
+                    float* msp_score, float* ml_score, float* pdf_score, float* msp_prob, float* max_logit,
+                    int* pred, float* ml_norm, float* scene_out, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POINTOPS_B200_H */

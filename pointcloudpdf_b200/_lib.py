@@ -1,0 +1,89 @@
+"""ctypes binding of libpointops_b200.so (the C ABI of include/pointops_b200.h).
+
+There is no CPU or eager-torch fallback behind this module: if the shared library is missing
+or cannot be loaded, every operator raises.  Build it with ``python -m pointcloudpdf_b200.build``
+(nvcc, sm_100a) -- ``__graft_entry__.build()`` does that.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import c_float, c_int, c_int64, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libpointops_b200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+P, I, L, F, Z = c_void_p, c_int, c_int64, c_float, c_size_t
+
+# name -> (restype, argtypes); mirrors include/pointops_b200.h line by line
+SIGNATURES = {
+    "pob_version": (I, []),
+    "pob_error_string": (ctypes.c_char_p, [I]),
+    "pob_knn_grid_workspace_bytes": (Z, [L, I, F]),
+    "pob_knn_grid_build": (I, [L, I, P, P, F, P, Z, P]),
+    "pob_knn_grid_query": (I, [L, I, L, I, P, P, P, F, P, P, P, P, I, P]),
+    "pob_knn_query": (I, [L, I, L, I, P, P, P, P, P, P, I, P, Z, P]),
+    "pob_knn_query_bruteforce": (I, [L, I, I, P, P, P, P, P, P, I, P, Z, P]),
+    "pob_farthest_point_sampling": (I, [I, L, P, P, P, P, P, I, P]),
+    "pob_grouping_forward": (I, [L, I, I, P, P, P, P]),
+    "pob_grouping_backward": (I, [L, I, I, P, P, P, P]),
+    "pob_subtraction_forward": (I, [L, I, I, P, P, P, P, P]),
+    "pob_subtraction_backward": (I, [L, I, I, P, P, P, P, P]),
+    "pob_aggregation_forward": (I, [L, I, I, I, P, P, P, P, P, P]),
+    "pob_aggregation_backward": (I, [L, I, I, I, P, P, P, P, P, P, P, P, P]),
+    "pob_interpolation_forward": (I, [L, I, I, P, P, P, P, P]),
+    "pob_interpolation_backward": (I, [L, I, I, P, P, P, P, P]),
+    "pob_group_xyz_forward": (I, [L, I, I, I, P, I, P, P, P, P, P]),
+    "pob_group_xyz_backward": (I, [L, I, I, I, P, P, P, P]),
+    "pob_score_workspace_bytes": (Z, [I]),
+    "pob_score_fused": (I, [L, I, I, P, P, P, F, P, P, P, P, P, P, P, P, P, Z, P]),
+}
+
+
+class PointopsB200Error(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the library once; raise loudly if it is absent (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise PointopsB200Error(
+                f"{LIB_PATH} is missing: the CUDA extension has not been built. Run "
+                "`python -m pointcloudpdf_b200.build` (needs nvcc; targets sm_100a). "
+                "pointcloudpdf_b200 has no CPU or eager fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def error_string(code: int) -> str:
+    return load().pob_error_string(int(code)).decode()
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        raise PointopsB200Error(f"{what} failed with code {code}: {error_string(code)}")
+
+
+def ptr(t) -> c_void_p:
+    """Device pointer of a tensor (None -> NULL)."""
+    return c_void_p(None) if t is None else c_void_p(t.data_ptr())
+
+
+def current_stream(device) -> c_void_p:
+    import torch
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)

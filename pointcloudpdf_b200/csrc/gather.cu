@@ -1,0 +1,658 @@
+// gather.cu -- the HBM-bound gather / scatter-add operators of the PTv1 path (sm_100a).
+//
+// Replaces the one-thread-per-scalar kernels of libs/pointops/src/{grouping,subtraction,
+// aggregation,interpolation}/*_cuda_kernel.cu (3 integer div/mod per element, idx re-read per
+// channel, 4-byte accesses, read-modify-write of the output in global memory, two scalar
+// atomics per element in backward) by row-vector kernels:
+//   * channels are moved as 128-bit vectors (float4 / red.global.add.v4.f32);
+//   * a warp owns whole neighbour rows: LPR = min(C/4, 32) lanes cover one row, 32/LPR rows are
+//     in flight per warp, so each 128-byte line of a gathered row is fetched by one request;
+//   * reductions over the neighbour axis (aggregation fwd, subtraction bwd) and over the
+//     share_planes axis (aggregation bwd, grad_weight) happen in registers + shuffles: no
+//     atomics and no output read-modify-write; only true scatters (grad of gathered rows) use
+//     vector atomics;
+//   * all index arithmetic is int64 (quirk C2: the reference overflows int above 2^31 elements).
+// The fast paths need C % 4 == 0 with C/4 a power of two (or a multiple of 32) -- every PTv1
+// width (32..512) qualifies; other shapes take the scalar kernels at the bottom, which are
+// still CUDA: there is no CPU fallback anywhere.
+#include "common.cuh"
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+namespace pob {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4_stream(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4_stream(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void red4(float* p, float4 v) {
+    atomicAdd(reinterpret_cast<float4*>(p), v);  // result unused -> RED.E.ADD.F32x4 (sm_90+)
+}
+__device__ __forceinline__ float4 f4_fma(float4 a, float4 b, float4 c) {
+    return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 f4_neg(float4 a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
+__device__ __forceinline__ float4 f4_shfl_xor(float4 v, int o) {
+    return make_float4(__shfl_xor_sync(FULL, v.x, o), __shfl_xor_sync(FULL, v.y, o), __shfl_xor_sync(FULL, v.z, o),
+                       __shfl_xor_sync(FULL, v.w, o));
+}
+
+// how a warp tiles rows of `cvec` float4: lpr lanes per row, spar rows side by side, chunks per lane
+struct RowTile {
+    int cvec, lpr, lpr_shift, spar, chunks;
+    bool ok;
+};
+static inline RowTile row_tile(int c) {
+    RowTile t = {};
+    t.ok = false;
+    if (c <= 0 || c % 4) return t;
+    t.cvec = c / 4;
+    if (t.cvec <= 32) {
+        if (t.cvec & (t.cvec - 1)) return t;
+        t.lpr = t.cvec;
+        t.chunks = 1;
+    } else {
+        if (t.cvec % 32) return t;
+        t.lpr = 32;
+        t.chunks = t.cvec / 32;
+    }
+    t.spar = 32 / t.lpr;
+    t.lpr_shift = 0;
+    while ((1 << t.lpr_shift) < t.lpr) t.lpr_shift++;
+    t.ok = true;
+    return t;
+}
+
+constexpr int GATHER_THREADS = 256;
+
+// ----------------------------------------------------------------------- grouping --
+// out[r, :] = in[idx[r], :]   r = m*ns + s      (grouping_cuda_kernel.cu:5-14)
+// SUB: out[r, :] = in1[r / ns, :] - in2[idx[r], :]   (subtraction_cuda_kernel.cu:5-16)
+template <bool SUB>
+__global__ void __launch_bounds__(GATHER_THREADS)
+gather_rows_kernel(int64_t rows, int ns, RowTile t, const float* __restrict__ in, const float* __restrict__ in1,
+                   const int* __restrict__ idx, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane >> t.lpr_shift, cl = lane & (t.lpr - 1);
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int U = 4;  // independent rows in flight per lane
+    const int64_t step = (int64_t)t.spar * U;
+    for (int64_t base = warp * step; base < rows; base += nwarps * step) {
+        int src[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t r = base + u * t.spar + sub;
+            src[u] = r < rows ? __ldg(idx + r) : -1;
+        }
+        for (int ch = 0; ch < t.chunks; ch++) {
+            const int cv = ch * t.lpr + cl;
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int64_t r = base + u * t.spar + sub;
+                if (r < rows) {
+                    v[u] = ld4(in + ((int64_t)src[u] * t.cvec + cv) * 4);
+                    if (SUB) v[u] = f4_sub(ld4(in1 + ((r / ns) * t.cvec + cv) * 4), v[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int64_t r = base + u * t.spar + sub;
+                if (r < rows) st4_stream(out + (r * t.cvec + cv) * 4, v[u]);
+            }
+        }
+    }
+}
+
+// grad_in[idx[r], :] += sign * grad_out[r, :]    (grouping_cuda_kernel.cu:16-25,
+// subtraction_cuda_kernel.cu:28-29 with sign = -1)
+__global__ void __launch_bounds__(GATHER_THREADS)
+scatter_rows_kernel(int64_t rows, RowTile t, float sign, const float* __restrict__ gout, const int* __restrict__ idx,
+                    float* __restrict__ gin) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane >> t.lpr_shift, cl = lane & (t.lpr - 1);
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int U = 4;
+    const int64_t step = (int64_t)t.spar * U;
+    for (int64_t base = warp * step; base < rows; base += nwarps * step) {
+        for (int ch = 0; ch < t.chunks; ch++) {
+            const int cv = ch * t.lpr + cl;
+            float4 v[U];
+            int dst[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int64_t r = base + u * t.spar + sub;
+                dst[u] = -1;
+                if (r < rows) { dst[u] = __ldg(idx + r); v[u] = ld4_stream(gout + (r * t.cvec + cv) * 4); }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (dst[u] >= 0) {
+                    float4 g = v[u];
+                    if (sign < 0.f) g = f4_neg(g);
+                    red4(gin + ((int64_t)dst[u] * t.cvec + cv) * 4, g);
+                }
+            }
+        }
+    }
+}
+
+// g1[n, :] = sum_s grad_out[n, s, :]   (subtraction_cuda_kernel.cu:28, without atomics)
+__global__ void __launch_bounds__(GATHER_THREADS)
+reduce_neighbours_kernel(int64_t n, int ns, RowTile t, const float* __restrict__ gout, float* __restrict__ g1) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane >> t.lpr_shift, cl = lane & (t.lpr - 1);
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = warp; p < n; p += nwarps) {
+        for (int ch = 0; ch < t.chunks; ch++) {
+            const int cv = ch * t.lpr + cl;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = sub; s < ns; s += t.spar) acc = f4_add(acc, ld4_stream(gout + ((p * ns + s) * t.cvec + cv) * 4));
+            for (int o = t.lpr; o < 32; o <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, o));
+            if (sub == 0) st4(g1 + (p * t.cvec + cv) * 4, acc);
+        }
+    }
+}
+
+// -------------------------------------------------------------------- aggregation --
+// out[n, c] = sum_s (in[idx[n,s], c] + pos[n,s,c]) * w[n,s,c % w_c]
+// (aggregation_cuda_kernel.cu:5-20).  One warp per point; spar neighbour rows in flight, the
+// partial sums meet in registers through shuffles; the output is written once.
+__global__ void __launch_bounds__(GATHER_THREADS)
+aggregation_fwd_kernel(int64_t n, int ns, RowTile t, int wvec, const float* __restrict__ in,
+                       const float* __restrict__ pos, const float* __restrict__ w, const int* __restrict__ idx,
+                       float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane >> t.lpr_shift, cl = lane & (t.lpr - 1);
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = warp; p < n; p += nwarps) {
+        for (int ch = 0; ch < t.chunks; ch++) {
+            const int cv = ch * t.lpr + cl;
+            const int wv = cv & (wvec - 1);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int s = sub; s < ns; s += t.spar) {
+                const int64_t r = p * ns + s;
+                const int src = __ldg(idx + r);
+                const float4 a = ld4(in + ((int64_t)src * t.cvec + cv) * 4);
+                const float4 b = ld4_stream(pos + (r * t.cvec + cv) * 4);
+                const float4 ww = ld4(w + (r * wvec + wv) * 4);
+                acc = f4_fma(f4_add(a, b), ww, acc);
+            }
+            for (int o = t.lpr; o < 32; o <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, o));
+            if (sub == 0) st4(out + (p * t.cvec + cv) * 4, acc);
+        }
+    }
+}
+
+// grad_in[idx[n,s], c] += g[n,c] * w[n,s,c%w_c]        (atomic scatter, vector red)
+// grad_pos[n,s,c]       = g[n,c] * w[n,s,c%w_c]        (streamed store)
+// grad_w[n,s,j]         = sum_{c%w_c==j} g[n,c] * (in[idx[n,s],c] + pos[n,s,c])   (shuffles)
+// (aggregation_cuda_kernel.cu:22-39)
+__global__ void __launch_bounds__(GATHER_THREADS)
+aggregation_bwd_kernel(int64_t n, int ns, RowTile t, int wvec, const float* __restrict__ in,
+                       const float* __restrict__ pos, const float* __restrict__ w, const int* __restrict__ idx,
+                       const float* __restrict__ gout, float* __restrict__ gin, float* __restrict__ gpos,
+                       float* __restrict__ gw) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane >> t.lpr_shift, cl = lane & (t.lpr - 1);
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = warp; p < n; p += nwarps) {
+        // all lanes take the same number of trips so the shuffles below stay convergent
+        for (int s0 = 0; s0 < ns; s0 += t.spar) {
+            const int s = s0 + sub;
+            const bool live = s < ns;
+            const int64_t r = p * ns + (live ? s : 0);
+            const int src = live ? __ldg(idx + r) : 0;
+            float4 gws = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int ch = 0; ch < t.chunks; ch++) {
+                const int cv = ch * t.lpr + cl;
+                const int wv = cv & (wvec - 1);
+                if (live) {
+                    const float4 g = ld4(gout + (p * t.cvec + cv) * 4);
+                    const float4 ww = ld4(w + (r * wvec + wv) * 4);
+                    const float4 a = ld4(in + ((int64_t)src * t.cvec + cv) * 4);
+                    const float4 b = ld4_stream(pos + (r * t.cvec + cv) * 4);
+                    const float4 gwv = f4_mul(g, ww);
+                    st4_stream(gpos + (r * t.cvec + cv) * 4, gwv);
+                    red4(gin + ((int64_t)src * t.cvec + cv) * 4, gwv);
+                    gws = f4_fma(g, f4_add(a, b), gws);
+                }
+            }
+            // lanes of one row whose cv agree modulo wvec share a weight vector
+            for (int o = wvec; o < t.lpr; o <<= 1) gws = f4_add(gws, f4_shfl_xor(gws, o));
+            if (live && cl < wvec) st4(gw + (r * wvec + cl) * 4, gws);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ interpolation --
+// out[n, c] = sum_{i<k} in[idx[n,i], c] * w[n,i]     (interpolation_cuda_kernel.cu:5-18)
+__global__ void __launch_bounds__(GATHER_THREADS)
+interpolation_fwd_kernel(int64_t n, int k, RowTile t, const float* __restrict__ in, const int* __restrict__ idx,
+                         const float* __restrict__ w, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane >> t.lpr_shift, cl = lane & (t.lpr - 1);
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp * t.spar; base < n; base += nwarps * t.spar) {
+        const int64_t p = base + sub;
+        if (p >= n) continue;
+        for (int ch = 0; ch < t.chunks; ch++) {
+            const int cv = ch * t.lpr + cl;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < k; i++) {
+                const int src = __ldg(idx + p * k + i);
+                const float wi = __ldg(w + p * k + i);
+                const float4 a = ld4(in + ((int64_t)src * t.cvec + cv) * 4);
+                acc = f4_fma(a, make_float4(wi, wi, wi, wi), acc);
+            }
+            st4_stream(out + (p * t.cvec + cv) * 4, acc);
+        }
+    }
+}
+
+// grad_in[idx[n,i], c] += g[n,c] * w[n,i]            (interpolation_cuda_kernel.cu:20-33)
+__global__ void __launch_bounds__(GATHER_THREADS)
+interpolation_bwd_kernel(int64_t n, int k, RowTile t, const float* __restrict__ gout, const int* __restrict__ idx,
+                         const float* __restrict__ w, float* __restrict__ gin) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane >> t.lpr_shift, cl = lane & (t.lpr - 1);
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = warp * t.spar; base < n; base += nwarps * t.spar) {
+        const int64_t p = base + sub;
+        if (p >= n) continue;
+        for (int ch = 0; ch < t.chunks; ch++) {
+            const int cv = ch * t.lpr + cl;
+            const float4 g = ld4_stream(gout + (p * t.cvec + cv) * 4);
+            for (int i = 0; i < k; i++) {
+                const int dst = __ldg(idx + p * k + i);
+                const float wi = __ldg(w + p * k + i);
+                red4(gin + ((int64_t)dst * t.cvec + cv) * 4, make_float4(g.x * wi, g.y * wi, g.z * wi, g.w * wi));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------ fused group-with-xyz (a3 semantics) --
+// out[m, s, :] = cat( (xyz[idx[m,s]] - new_xyz[m]) * [idx>=0] , feat[idx[m,s]] * [idx>=0] )
+// (functions/grouping.py:36-60: five torch passes there, one here).  feat may be f32/f16/bf16;
+// the output is f32 (the reference's cat with an f32 zero row promotes).  One warp per query m
+// walks the contiguous ns*(3+C) output floats, so stores are fully coalesced.
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(GATHER_THREADS)
+group_xyz_fwd_kernel(int64_t m, int ns, int c, int with_xyz, const T* __restrict__ feat, const float* __restrict__ xyz,
+                     const float* __restrict__ new_xyz, const int* __restrict__ idx, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int x = with_xyz ? 3 : 0;
+    const int W = x + c;
+    const int per = ns * W;
+    for (int64_t q = warp; q < m; q += nwarps) {
+        float nq[3] = {0.f, 0.f, 0.f};
+        if (with_xyz) { nq[0] = __ldg(new_xyz + q * 3); nq[1] = __ldg(new_xyz + q * 3 + 1); nq[2] = __ldg(new_xyz + q * 3 + 2); }
+        float* o = out + q * per;
+        const int* iq = idx + q * ns;
+        int s = lane / W, chn = lane % W;
+        for (int f = lane; f < per; f += 32) {
+            const int src = __ldg(iq + s);
+            float v = 0.f;
+            if (src >= 0) {
+                if (chn < x) v = __fsub_rn(__ldg(xyz + (int64_t)src * 3 + chn), chn == 0 ? nq[0] : (chn == 1 ? nq[1] : nq[2]));
+                else v = to_f32<T>(feat[(int64_t)src * c + (chn - x)]);
+            }
+            __stcs(o + f, v);
+            chn += 32;
+            while (chn >= W) { chn -= W; s++; }
+        }
+    }
+}
+
+// grad_feat[idx[m,s], c] += grad_out[m, s, coff + c]  for idx >= 0   (autograd of the torch
+// indexing in functions/grouping.py:43-45; xyz gets no gradient)
+__global__ void __launch_bounds__(GATHER_THREADS)
+group_xyz_bwd_kernel(int64_t m, int ns, int c, int coff, const float* __restrict__ gout, const int* __restrict__ idx,
+                     float* __restrict__ gfeat) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int W = coff + c;
+    const int per = ns * W;
+    for (int64_t q = warp; q < m; q += nwarps) {
+        const float* g = gout + q * per;
+        const int* iq = idx + q * ns;
+        int s = lane / W, chn = lane % W;
+        for (int f = lane; f < per; f += 32) {
+            const int dst = __ldg(iq + s);
+            if (dst >= 0 && chn >= coff) atomicAdd(gfeat + (int64_t)dst * c + (chn - coff), __ldcs(g + f));
+            chn += 32;
+            while (chn >= W) { chn -= W; s++; }
+        }
+    }
+}
+
+// ------------------------------------------------------- scalar kernels (any shape) --
+__global__ void gather_rows_scalar_kernel(int64_t total, int ns, int c, int sub, const float* __restrict__ in,
+                                          const float* __restrict__ in1, const int* __restrict__ idx,
+                                          float* __restrict__ out) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / c;
+        const int ch = (int)(e - r * c);
+        float v = __ldg(in + (int64_t)__ldg(idx + r) * c + ch);
+        if (sub) v = __ldg(in1 + (r / ns) * c + ch) - v;
+        out[e] = v;
+    }
+}
+
+__global__ void scatter_rows_scalar_kernel(int64_t total, int c, float sign, const float* __restrict__ gout,
+                                           const int* __restrict__ idx, float* __restrict__ gin) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / c;
+        const int ch = (int)(e - r * c);
+        atomicAdd(gin + (int64_t)__ldg(idx + r) * c + ch, sign * gout[e]);
+    }
+}
+
+__global__ void reduce_neighbours_scalar_kernel(int64_t n, int ns, int c, const float* __restrict__ gout,
+                                                float* __restrict__ g1) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n * c; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = e / c;
+        const int ch = (int)(e - p * c);
+        float acc = 0.f;
+        for (int s = 0; s < ns; s++) acc += gout[(p * ns + s) * c + ch];
+        g1[e] = acc;
+    }
+}
+
+__global__ void aggregation_fwd_scalar_kernel(int64_t n, int ns, int c, int w_c, const float* __restrict__ in,
+                                              const float* __restrict__ pos, const float* __restrict__ w,
+                                              const int* __restrict__ idx, float* __restrict__ out) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n * c; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = e / c;
+        const int ch = (int)(e - p * c);
+        float acc = 0.f;
+        for (int s = 0; s < ns; s++) {
+            const int64_t r = p * ns + s;
+            acc = fmaf(__ldg(in + (int64_t)__ldg(idx + r) * c + ch) + pos[r * c + ch], __ldg(w + r * w_c + ch % w_c), acc);
+        }
+        out[e] = acc;
+    }
+}
+
+// grad_weight must be zero on entry for this path (atomics over the share_planes channels)
+__global__ void aggregation_bwd_scalar_kernel(int64_t n, int ns, int c, int w_c, const float* __restrict__ in,
+                                              const float* __restrict__ pos, const float* __restrict__ w,
+                                              const int* __restrict__ idx, const float* __restrict__ gout,
+                                              float* __restrict__ gin, float* __restrict__ gpos,
+                                              float* __restrict__ gw) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n * c; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = e / c;
+        const int ch = (int)(e - p * c);
+        const float g = gout[e];
+        for (int s = 0; s < ns; s++) {
+            const int64_t r = p * ns + s;
+            const int64_t ii = (int64_t)__ldg(idx + r) * c + ch;
+            const float wt = __ldg(w + r * w_c + ch % w_c);
+            atomicAdd(gin + ii, g * wt);
+            gpos[r * c + ch] = g * wt;
+            atomicAdd(gw + r * w_c + ch % w_c, g * (__ldg(in + ii) + pos[r * c + ch]));
+        }
+    }
+}
+
+__global__ void interpolation_fwd_scalar_kernel(int64_t n, int c, int k, const float* __restrict__ in,
+                                                const int* __restrict__ idx, const float* __restrict__ w,
+                                                float* __restrict__ out) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n * c; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = e / c;
+        const int ch = (int)(e - p * c);
+        float acc = 0.f;
+        for (int i = 0; i < k; i++) acc = fmaf(__ldg(in + (int64_t)__ldg(idx + p * k + i) * c + ch), __ldg(w + p * k + i), acc);
+        out[e] = acc;
+    }
+}
+
+__global__ void interpolation_bwd_scalar_kernel(int64_t n, int c, int k, const float* __restrict__ gout,
+                                                const int* __restrict__ idx, const float* __restrict__ w,
+                                                float* __restrict__ gin) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n * c; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = e / c;
+        const int ch = (int)(e - p * c);
+        for (int i = 0; i < k; i++) atomicAdd(gin + (int64_t)__ldg(idx + p * k + i) * c + ch, gout[e] * __ldg(w + p * k + i));
+    }
+}
+
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+// warps needed -> CTAs, capped at a few waves of the machine
+static inline unsigned warp_grid(int64_t warps_needed) {
+    return grid_for(warps_needed * 32, GATHER_THREADS, 8, 4);
+}
+
+}  // namespace pob
+
+using namespace pob;
+
+// ===================================================================== C ABI ==
+
+// grouping_forward_cuda_launcher(m, nsample, c, input, idx, output)  (grouping_cuda_kernel.h:14)
+POB_API int pob_grouping_forward(int64_t m, int nsample, int c, const float* input, const int* idx, float* output,
+                                 cudaStream_t stream) {
+    if (m < 0 || nsample < 1 || c < 1) return POB_ERR_BAD_ARG;
+    const int64_t rows = m * nsample;
+    if (rows == 0) return 0;
+    if (!input || !idx || !output) return POB_ERR_BAD_ARG;
+    const RowTile t = row_tile(c);
+    if (t.ok && aligned16(input) && aligned16(output)) {
+        gather_rows_kernel<false><<<warp_grid(ceil_div(rows, t.spar * 4)), GATHER_THREADS, 0, stream>>>(
+            rows, nsample, t, input, nullptr, idx, output);
+    } else {
+        gather_rows_scalar_kernel<<<grid_for(rows * c, 256, 8), 256, 0, stream>>>(rows * c, nsample, c, 0, input,
+                                                                                  nullptr, idx, output);
+    }
+    POB_RETURN_LAST_ERROR();
+}
+
+// grouping_backward_cuda_launcher(m, nsample, c, grad_output, idx, grad_input)  (grouping_cuda_kernel.h:15)
+// grad_input is accumulated into (the caller zeroes it, as functions/grouping.py:31 does).
+POB_API int pob_grouping_backward(int64_t m, int nsample, int c, const float* grad_output, const int* idx,
+                                  float* grad_input, cudaStream_t stream) {
+    if (m < 0 || nsample < 1 || c < 1) return POB_ERR_BAD_ARG;
+    const int64_t rows = m * nsample;
+    if (rows == 0) return 0;
+    if (!grad_output || !idx || !grad_input) return POB_ERR_BAD_ARG;
+    const RowTile t = row_tile(c);
+    if (t.ok && aligned16(grad_output) && aligned16(grad_input)) {
+        scatter_rows_kernel<<<warp_grid(ceil_div(rows, t.spar * 4)), GATHER_THREADS, 0, stream>>>(
+            rows, t, 1.f, grad_output, idx, grad_input);
+    } else {
+        scatter_rows_scalar_kernel<<<grid_for(rows * c, 256, 8), 256, 0, stream>>>(rows * c, c, 1.f, grad_output, idx,
+                                                                                   grad_input);
+    }
+    POB_RETURN_LAST_ERROR();
+}
+
+// subtraction_forward_cuda_launcher(n, nsample, c, input1, input2, idx, output)  (subtraction_cuda_kernel.h:14)
+POB_API int pob_subtraction_forward(int64_t n, int nsample, int c, const float* input1, const float* input2,
+                                    const int* idx, float* output, cudaStream_t stream) {
+    if (n < 0 || nsample < 1 || c < 1) return POB_ERR_BAD_ARG;
+    const int64_t rows = n * nsample;
+    if (rows == 0) return 0;
+    if (!input1 || !input2 || !idx || !output) return POB_ERR_BAD_ARG;
+    const RowTile t = row_tile(c);
+    if (t.ok && aligned16(input1) && aligned16(input2) && aligned16(output)) {
+        gather_rows_kernel<true><<<warp_grid(ceil_div(rows, t.spar * 4)), GATHER_THREADS, 0, stream>>>(
+            rows, nsample, t, input2, input1, idx, output);
+    } else {
+        gather_rows_scalar_kernel<<<grid_for(rows * c, 256, 8), 256, 0, stream>>>(rows * c, nsample, c, 1, input2,
+                                                                                  input1, idx, output);
+    }
+    POB_RETURN_LAST_ERROR();
+}
+
+// subtraction_backward_cuda_launcher(n, nsample, c, idx, grad_output, grad_input1, grad_input2)
+// (subtraction_cuda_kernel.h:15).  grad_input1 is overwritten; grad_input2 is accumulated into.
+POB_API int pob_subtraction_backward(int64_t n, int nsample, int c, const int* idx, const float* grad_output,
+                                     float* grad_input1, float* grad_input2, cudaStream_t stream) {
+    if (n < 0 || nsample < 1 || c < 1) return POB_ERR_BAD_ARG;
+    const int64_t rows = n * nsample;
+    if (rows == 0) return 0;
+    if (!idx || !grad_output || !grad_input1 || !grad_input2) return POB_ERR_BAD_ARG;
+    const RowTile t = row_tile(c);
+    if (t.ok && aligned16(grad_output) && aligned16(grad_input1) && aligned16(grad_input2)) {
+        reduce_neighbours_kernel<<<warp_grid(n), GATHER_THREADS, 0, stream>>>(n, nsample, t, grad_output, grad_input1);
+        scatter_rows_kernel<<<warp_grid(ceil_div(rows, t.spar * 4)), GATHER_THREADS, 0, stream>>>(
+            rows, t, -1.f, grad_output, idx, grad_input2);
+    } else {
+        reduce_neighbours_scalar_kernel<<<grid_for(n * c, 256, 8), 256, 0, stream>>>(n, nsample, c, grad_output,
+                                                                                     grad_input1);
+        scatter_rows_scalar_kernel<<<grid_for(rows * c, 256, 8), 256, 0, stream>>>(rows * c, c, -1.f, grad_output, idx,
+                                                                                   grad_input2);
+    }
+    POB_RETURN_LAST_ERROR();
+}
+
+static inline bool agg_fast(const RowTile& t, int c, int w_c, int* wvec) {
+    if (!t.ok || w_c < 4 || w_c % 4 || c % w_c) return false;
+    const int v = w_c / 4;
+    if (v & (v - 1)) return false;
+    if (v > t.lpr) return false;
+    *wvec = v;
+    return true;
+}
+
+// aggregation_forward_cuda_launcher(n, nsample, c, w_c, input, position, weight, idx, output)
+// (aggregation_cuda_kernel.h:14).  output is overwritten (the reference accumulates into a
+// zeroed buffer, functions/aggregation.py:21).
+POB_API int pob_aggregation_forward(int64_t n, int nsample, int c, int w_c, const float* input, const float* position,
+                                    const float* weight, const int* idx, float* output, cudaStream_t stream) {
+    if (n < 0 || nsample < 1 || c < 1 || w_c < 1) return POB_ERR_BAD_ARG;
+    if (n == 0) return 0;
+    if (!input || !position || !weight || !idx || !output) return POB_ERR_BAD_ARG;
+    const RowTile t = row_tile(c);
+    int wvec = 0;
+    if (agg_fast(t, c, w_c, &wvec) && aligned16(input) && aligned16(position) && aligned16(weight) && aligned16(output)) {
+        aggregation_fwd_kernel<<<warp_grid(n), GATHER_THREADS, 0, stream>>>(n, nsample, t, wvec, input, position,
+                                                                            weight, idx, output);
+    } else {
+        aggregation_fwd_scalar_kernel<<<grid_for(n * c, 256, 8), 256, 0, stream>>>(n, nsample, c, w_c, input, position,
+                                                                                   weight, idx, output);
+    }
+    POB_RETURN_LAST_ERROR();
+}
+
+// aggregation_backward_cuda_launcher(...)  (aggregation_cuda_kernel.h:15).  grad_input is
+// accumulated into (zeroed by the caller); grad_position and grad_weight are overwritten
+// (grad_weight is zeroed here first on the scalar path, which still needs atomics).
+POB_API int pob_aggregation_backward(int64_t n, int nsample, int c, int w_c, const float* input,
+                                     const float* position, const float* weight, const int* idx,
+                                     const float* grad_output, float* grad_input, float* grad_position,
+                                     float* grad_weight, cudaStream_t stream) {
+    if (n < 0 || nsample < 1 || c < 1 || w_c < 1) return POB_ERR_BAD_ARG;
+    if (n == 0) return 0;
+    if (!input || !position || !weight || !idx || !grad_output || !grad_input || !grad_position || !grad_weight)
+        return POB_ERR_BAD_ARG;
+    const RowTile t = row_tile(c);
+    int wvec = 0;
+    if (agg_fast(t, c, w_c, &wvec) && aligned16(input) && aligned16(position) && aligned16(weight) &&
+        aligned16(grad_output) && aligned16(grad_input) && aligned16(grad_position) && aligned16(grad_weight)) {
+        aggregation_bwd_kernel<<<warp_grid(n), GATHER_THREADS, 0, stream>>>(
+            n, nsample, t, wvec, input, position, weight, idx, grad_output, grad_input, grad_position, grad_weight);
+    } else {
+        POB_CHECK(cudaMemsetAsync(grad_weight, 0, sizeof(float) * (size_t)n * nsample * w_c, stream));
+        aggregation_bwd_scalar_kernel<<<grid_for(n * c, 256, 8), 256, 0, stream>>>(
+            n, nsample, c, w_c, input, position, weight, idx, grad_output, grad_input, grad_position, grad_weight);
+    }
+    POB_RETURN_LAST_ERROR();
+}
+
+// interpolation_forward_cuda_launcher(n, c, k, input, idx, weight, output)  (interpolation_cuda_kernel.h:14)
+// output is overwritten.
+POB_API int pob_interpolation_forward(int64_t n, int c, int k, const float* input, const int* idx, const float* weight,
+                                      float* output, cudaStream_t stream) {
+    if (n < 0 || c < 1 || k < 1) return POB_ERR_BAD_ARG;
+    if (n == 0) return 0;
+    if (!input || !idx || !weight || !output) return POB_ERR_BAD_ARG;
+    const RowTile t = row_tile(c);
+    if (t.ok && aligned16(input) && aligned16(output)) {
+        interpolation_fwd_kernel<<<warp_grid(ceil_div(n, t.spar)), GATHER_THREADS, 0, stream>>>(n, k, t, input, idx,
+                                                                                                weight, output);
+    } else {
+        interpolation_fwd_scalar_kernel<<<grid_for(n * c, 256, 8), 256, 0, stream>>>(n, c, k, input, idx, weight, output);
+    }
+    POB_RETURN_LAST_ERROR();
+}
+
+// interpolation_backward_cuda_launcher(n, c, k, grad_output, idx, weight, grad_input)
+// (interpolation_cuda_kernel.h:15).  grad_input is accumulated into.
+POB_API int pob_interpolation_backward(int64_t n, int c, int k, const float* grad_output, const int* idx,
+                                       const float* weight, float* grad_input, cudaStream_t stream) {
+    if (n < 0 || c < 1 || k < 1) return POB_ERR_BAD_ARG;
+    if (n == 0) return 0;
+    if (!grad_output || !idx || !weight || !grad_input) return POB_ERR_BAD_ARG;
+    const RowTile t = row_tile(c);
+    if (t.ok && aligned16(grad_output) && aligned16(grad_input)) {
+        interpolation_bwd_kernel<<<warp_grid(ceil_div(n, t.spar)), GATHER_THREADS, 0, stream>>>(n, k, t, grad_output,
+                                                                                                idx, weight, grad_input);
+    } else {
+        interpolation_bwd_scalar_kernel<<<grid_for(n * c, 256, 8), 256, 0, stream>>>(n, c, k, grad_output, idx, weight,
+                                                                                     grad_input);
+    }
+    POB_RETURN_LAST_ERROR();
+}
+
+// Fused replacement for pointops.grouping (functions/grouping.py:36-60).  feat_dtype: 0 f32,
+// 1 f16, 2 bf16.  output is (m, nsample, 3 + c) f32 when with_xyz, else (m, nsample, c).
+POB_API int pob_group_xyz_forward(int64_t m, int nsample, int c, int with_xyz, const void* feat, int feat_dtype,
+                                  const float* xyz, const float* new_xyz, const int* idx, float* output,
+                                  cudaStream_t stream) {
+    if (m < 0 || nsample < 1 || c < 1 || feat_dtype < 0 || feat_dtype > 2) return POB_ERR_BAD_ARG;
+    if (m == 0) return 0;
+    if (!feat || !idx || !output || (with_xyz && (!xyz || !new_xyz))) return POB_ERR_BAD_ARG;
+    const unsigned grid = warp_grid(m);
+    if (feat_dtype == 0)
+        group_xyz_fwd_kernel<float><<<grid, GATHER_THREADS, 0, stream>>>(m, nsample, c, with_xyz, (const float*)feat, xyz,
+                                                                        new_xyz, idx, output);
+    else if (feat_dtype == 1)
+        group_xyz_fwd_kernel<__half><<<grid, GATHER_THREADS, 0, stream>>>(m, nsample, c, with_xyz, (const __half*)feat,
+                                                                         xyz, new_xyz, idx, output);
+    else
+        group_xyz_fwd_kernel<__nv_bfloat16><<<grid, GATHER_THREADS, 0, stream>>>(
+            m, nsample, c, with_xyz, (const __nv_bfloat16*)feat, xyz, new_xyz, idx, output);
+    POB_RETURN_LAST_ERROR();
+}
+
+// Backward of the above w.r.t. feat: grad_feat (n, c) f32, accumulated into (caller zeroes).
+// grad_output is (m, nsample, coff + c) with coff = 3 when the forward used with_xyz.
+POB_API int pob_group_xyz_backward(int64_t m, int nsample, int c, int with_xyz, const float* grad_output,
+                                   const int* idx, float* grad_feat, cudaStream_t stream) {
+    if (m < 0 || nsample < 1 || c < 1) return POB_ERR_BAD_ARG;
+    if (m == 0) return 0;
+    if (!grad_output || !idx || !grad_feat) return POB_ERR_BAD_ARG;
+    group_xyz_bwd_kernel<<<warp_grid(m), GATHER_THREADS, 0, stream>>>(m, nsample, c, with_xyz ? 3 : 0, grad_output, idx,
+                                                                      grad_feat);
+    POB_RETURN_LAST_ERROR();
+}

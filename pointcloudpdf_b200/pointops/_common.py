@@ -1,0 +1,220 @@
+"""Host-side plumbing shared by the operator wrappers: argument validation, the host mirror of
+offset tensors (so wrappers never read device memory back), and the neighbour-grid cache."""
+from __future__ import annotations
+
+import os
+import threading
+from collections import OrderedDict
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from .. import _lib
+
+
+# --------------------------------------------------------------------------- validation --
+
+def require(t: torch.Tensor, name: str, dtype=None, dim: Optional[int] = None, last: Optional[int] = None):
+    """Device / dtype / layout checks the reference leaves to chance (SURVEY.md 8b 'Errors')."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (pointcloudpdf_b200 has no CPU path), got {t.device}")
+    if dtype is not None:
+        dtypes = dtype if isinstance(dtype, (tuple, list)) else (dtype,)
+        if t.dtype not in dtypes:
+            raise TypeError(f"{name} must have dtype {' or '.join(str(d) for d in dtypes)}, got {t.dtype}")
+    if dim is not None and t.dim() != dim:
+        raise ValueError(f"{name} must be {dim}-dimensional, got shape {tuple(t.shape)}")
+    if last is not None and t.shape[-1] != last:
+        raise ValueError(f"{name} must have last dimension {last}, got shape {tuple(t.shape)}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def same_device(*named):
+    dev = None
+    for name, t in named:
+        if t is None:
+            continue
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError(f"{name} is on {t.device}, expected {dev}")
+    return dev
+
+
+def offset_i32(offset: torch.Tensor, name: str = "offset") -> torch.Tensor:
+    """The reference casts with .int() at every call (functions/query.py:22)."""
+    if not isinstance(offset, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not offset.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor, got {offset.device}")
+    if offset.dtype not in (torch.int32, torch.int64):
+        raise TypeError(f"{name} must be int32 or int64, got {offset.dtype}")
+    if offset.dim() != 1 or offset.numel() < 1:
+        raise ValueError(f"{name} must be a non-empty 1-d tensor of cumulative counts")
+    if offset.dtype == torch.int32 and offset.is_contiguous():
+        return offset
+    out = offset.to(torch.int32).contiguous()
+    known = _HOST.get(_key(offset))
+    if known is not None:
+        register_host_offset(out, known[1])
+    return out
+
+
+# ------------------------------------------------------------ host mirror of offsets ------
+# FPS needs the largest scene size and the total sample count on the host.  The reference gets
+# them by indexing CUDA tensors in python loops (functions/sampling.py:15-18: one sync per
+# scene).  Callers that already know the values (our PTv1 mirror, the bench harness) register
+# them; otherwise the first use costs one .tolist() and is remembered while the tensor lives.
+
+_HOST: "OrderedDict[Tuple, Tuple[torch.Tensor, List[int]]]" = OrderedDict()
+_HOST_MAX = 256
+_host_lock = threading.Lock()
+
+
+def _key(t: torch.Tensor) -> Tuple:
+    return (t.data_ptr(), t._version, t.dtype, tuple(t.shape), t.device.index)
+
+
+def register_host_offset(t: torch.Tensor, values: Sequence[int]) -> torch.Tensor:
+    vals = [int(v) for v in values]
+    if len(vals) != t.numel():
+        raise ValueError("host values do not match the offset tensor's length")
+    with _host_lock:
+        _HOST[_key(t)] = (t, vals)  # holding t keeps its storage (and data_ptr) from being recycled
+        while len(_HOST) > _HOST_MAX:
+            _HOST.popitem(last=False)
+    return t
+
+
+def host_offset(t: torch.Tensor) -> List[int]:
+    k = _key(t)
+    with _host_lock:
+        hit = _HOST.get(k)
+        if hit is not None:
+            _HOST.move_to_end(k)
+            return hit[1]
+    vals = t.tolist()  # device sync, once per offset tensor
+    register_host_offset(t, vals)
+    return vals
+
+
+def scene_sizes(vals: Sequence[int]) -> List[int]:
+    return [e - s for s, e in zip([0] + list(vals[:-1]), vals)]
+
+
+# ------------------------------------------------------------------- neighbour grid -------
+
+CELL_PTS = float(os.environ.get("POINTOPS_B200_CELL_PTS", "2.0"))
+_GRID_CACHE_SIZE = int(os.environ.get("POINTOPS_B200_GRID_CACHE", "8"))
+_KNN_CACHE_SIZE = int(os.environ.get("POINTOPS_B200_KNN_CACHE", "8"))
+
+
+class NeighbourGrid:
+    """Device-resident uniform grid over (xyz, offset): the workspace pob_knn_grid_build fills."""
+
+    def __init__(self, xyz: torch.Tensor, offset: torch.Tensor, cell_pts: float = CELL_PTS):
+        lib = _lib.load()
+        self.xyz, self.offset = xyz, offset  # keep alive: the grid indexes into them
+        self.n, self.b, self.cell_pts = int(xyz.shape[0]), int(offset.numel()), float(cell_pts)
+        nbytes = lib.pob_knn_grid_workspace_bytes(self.n, self.b, self.cell_pts)
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=xyz.device)
+        rc = lib.pob_knn_grid_build(self.n, self.b, _lib.ptr(xyz), _lib.ptr(offset), self.cell_pts,
+                                    _lib.ptr(self.workspace), nbytes, _lib.current_stream(xyz.device))
+        _lib.check(rc, "pob_knn_grid_build")
+
+    def query(self, nsample: int, new_xyz: torch.Tensor, new_offset: torch.Tensor, want_dist=True, want_weight=False):
+        lib = _lib.load()
+        m = int(new_xyz.shape[0])
+        dev = new_xyz.device
+        idx = torch.empty((m, nsample), dtype=torch.int32, device=dev)
+        dist = torch.empty((m, nsample), dtype=torch.float32, device=dev) if want_dist else None
+        weight = torch.empty((m, nsample), dtype=torch.float32, device=dev) if want_weight else None
+        rc = lib.pob_knn_grid_query(m, int(nsample), self.n, self.b, _lib.ptr(self.xyz), _lib.ptr(new_xyz),
+                                    _lib.ptr(new_offset), self.cell_pts, _lib.ptr(self.workspace), _lib.ptr(idx),
+                                    _lib.ptr(dist), _lib.ptr(weight), 1, _lib.current_stream(dev))
+        _lib.check(rc, "pob_knn_grid_query")
+        return idx, dist, weight
+
+
+class _LRU:
+    def __init__(self, size: int):
+        self.size, self.d, self.lock = size, OrderedDict(), threading.Lock()
+
+    def get(self, k):
+        if self.size <= 0:
+            return None
+        with self.lock:
+            v = self.d.get(k)
+            if v is not None:
+                self.d.move_to_end(k)
+            return v
+
+    def put(self, k, v):
+        if self.size <= 0:
+            return
+        with self.lock:
+            self.d[k] = v
+            while len(self.d) > self.size:
+                self.d.popitem(last=False)
+
+    def clear(self):
+        with self.lock:
+            self.d.clear()
+
+
+_grids = _LRU(_GRID_CACHE_SIZE)
+_knn_results = _LRU(_KNN_CACHE_SIZE)
+
+
+def _stream_id(dev) -> int:
+    return int(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def get_grid(xyz: torch.Tensor, offset: torch.Tensor) -> NeighbourGrid:
+    """Grid for (xyz, offset), reused while both tensors are unchanged (same storage, same
+    torch version counter) on the same stream: within one PTv1 stage the same cloud is searched
+    by every block, by the next TransitionDown and by the decoder's interpolation."""
+    k = (_key(xyz), _key(offset), _stream_id(xyz.device))
+    g = _grids.get(k)
+    if g is None:
+        g = NeighbourGrid(xyz, offset)
+        _grids.put(k, g)
+    return g
+
+
+def cached_knn(nsample: int, xyz, offset, new_xyz, new_offset, want_weight=False):
+    """(idx, dist[, weight]) with reuse of identical queries (PTv1 recomputes the same self-kNN
+    in every block of a stage, point_transformer_seg.py:51; PTv2 in the same codebase already
+    shares it).  Cached outputs are handed out again only if nobody wrote into them."""
+    k = (int(nsample), bool(want_weight), _key(xyz), _key(offset), _key(new_xyz), _key(new_offset),
+         _stream_id(xyz.device))
+    hit = _knn_results.get(k)
+    if hit is not None:
+        outs, versions, _keep = hit
+        if all(o is None or o._version == v for o, v in zip(outs, versions)):
+            return outs
+    outs = get_grid(xyz, offset).query(nsample, new_xyz, new_offset, True, want_weight)
+    # the entry keeps the key tensors alive, so their data_ptr cannot be recycled under the key
+    _knn_results.put(k, (outs, tuple(-1 if o is None else o._version for o in outs),
+                         (xyz, offset, new_xyz, new_offset)))
+    return outs
+
+
+def clear_caches() -> None:
+    """Drop cached grids / kNN results / host offsets (frees the tensors they keep alive)."""
+    _grids.clear()
+    _knn_results.clear()
+    with _host_lock:
+        _HOST.clear()
+
+
+def set_cache_sizes(grid: Optional[int] = None, knn: Optional[int] = None) -> None:
+    if grid is not None:
+        _grids.size = int(grid)
+    if knn is not None:
+        _knn_results.size = int(knn)
+    clear_caches()

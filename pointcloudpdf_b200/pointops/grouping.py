@@ -1,0 +1,99 @@
+"""grouping / grouping2 -- mirror of libs/pointops/functions/grouping.py."""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from .. import _lib
+from . import _common as C
+
+_DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+class Grouping(Function):
+    """pointops.grouping2 (functions/grouping.py:7-33): plain gather, f32, idx >= 0."""
+
+    @staticmethod
+    def forward(ctx, input, idx):
+        """input: (n, c) f32, idx: (m, nsample) i32 -> (m, nsample, c)"""
+        C.require(input, "input", torch.float32, 2)
+        C.require(idx, "idx", torch.int32, 2)
+        C.same_device(("input", input), ("idx", idx))
+        m, nsample = idx.shape
+        n, c = input.shape
+        output = torch.empty((m, nsample, c), dtype=torch.float32, device=input.device)
+        with torch.cuda.device(input.device):
+            rc = _lib.load().pob_grouping_forward(m, nsample, c, _lib.ptr(input), _lib.ptr(idx), _lib.ptr(output),
+                                                  _lib.current_stream(input.device))
+        _lib.check(rc, "pob_grouping_forward")
+        ctx.n = n
+        ctx.save_for_backward(idx)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (idx,) = ctx.saved_tensors
+        grad_output = grad_output.contiguous().float()
+        m, nsample, c = grad_output.shape
+        grad_input = torch.zeros((ctx.n, c), dtype=torch.float32, device=grad_output.device)
+        with torch.cuda.device(grad_output.device):
+            rc = _lib.load().pob_grouping_backward(m, nsample, c, _lib.ptr(grad_output), _lib.ptr(idx),
+                                                   _lib.ptr(grad_input), _lib.current_stream(grad_output.device))
+        _lib.check(rc, "pob_grouping_backward")
+        return grad_input, None
+
+
+grouping2 = Grouping.apply
+
+
+class _GroupXYZ(Function):
+    """The torch-level pointops.grouping (functions/grouping.py:36-60) as one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, feat, idx, xyz, new_xyz, with_xyz):
+        m, nsample = idx.shape
+        n, c = feat.shape
+        width = c + (3 if with_xyz else 0)
+        out = torch.empty((m, nsample, width), dtype=torch.float32, device=feat.device)
+        with torch.cuda.device(feat.device):
+            rc = _lib.load().pob_group_xyz_forward(m, nsample, c, 1 if with_xyz else 0, _lib.ptr(feat),
+                                                   _DTYPE_CODE[feat.dtype], _lib.ptr(xyz), _lib.ptr(new_xyz),
+                                                   _lib.ptr(idx), _lib.ptr(out), _lib.current_stream(feat.device))
+        _lib.check(rc, "pob_group_xyz_forward")
+        ctx.shape = (n, c, bool(with_xyz), feat.dtype)
+        ctx.save_for_backward(idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        n, c, with_xyz, dtype = ctx.shape
+        grad_out = grad_out.contiguous().float()
+        m, nsample = idx.shape
+        grad_feat = torch.zeros((n, c), dtype=torch.float32, device=grad_out.device)
+        with torch.cuda.device(grad_out.device):
+            rc = _lib.load().pob_group_xyz_backward(m, nsample, c, 1 if with_xyz else 0, _lib.ptr(grad_out),
+                                                    _lib.ptr(idx), _lib.ptr(grad_feat),
+                                                    _lib.current_stream(grad_out.device))
+        _lib.check(rc, "pob_group_xyz_backward")
+        return grad_feat.to(dtype), None, None, None, None
+
+
+def grouping(idx, feat, xyz, new_xyz=None, with_xyz=False):
+    """pointops.grouping(idx, feat, xyz, new_xyz=None, with_xyz=False)
+    (functions/grouping.py:36-60): gather with idx -1 -> zero row; with_xyz prepends
+    (xyz[idx] - new_xyz[m]) masked the same way.  feat may be f32/f16/bf16; the result is f32
+    (the reference's cat with an f32 zero row promotes).  Differentiable w.r.t. feat."""
+    if new_xyz is None:
+        new_xyz = xyz
+    C.require(idx, "idx", torch.int32, 2)
+    C.require(feat, "feat", tuple(_DTYPE_CODE), 2)
+    C.require(xyz, "xyz", torch.float32, 2, 3)
+    C.same_device(("idx", idx), ("feat", feat), ("xyz", xyz), ("new_xyz", new_xyz))
+    if with_xyz:
+        C.require(new_xyz, "new_xyz", torch.float32, 2, 3)
+        if new_xyz.shape[0] != idx.shape[0]:
+            raise ValueError("new_xyz and idx must have the same number of rows")
+    if feat.shape[0] != xyz.shape[0]:
+        raise ValueError("feat and xyz must have the same number of rows")
+    return _GroupXYZ.apply(feat, idx, xyz, new_xyz, bool(with_xyz))

@@ -1,0 +1,44 @@
+"""farthest_point_sampling -- mirror of libs/pointops/functions/sampling.py:7-27."""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from .. import _lib
+from . import _common as C
+
+
+class FarthestPointSampling(Function):
+    @staticmethod
+    def forward(ctx, xyz, offset, new_offset):
+        """
+        input: xyz (n, 3) f32, offset (b), new_offset (b) cumulative sample counts
+        output: idx (new_offset[-1]) i32, global row indices, scene-major
+        """
+        C.require(xyz, "xyz", torch.float32, 2, 3)
+        offset, new_offset = C.offset_i32(offset, "offset"), C.offset_i32(new_offset, "new_offset")
+        C.same_device(("xyz", xyz), ("offset", offset), ("new_offset", new_offset))
+        b = offset.numel()
+        if new_offset.numel() != b:
+            raise ValueError("offset and new_offset must describe the same number of scenes")
+        # the two host numbers the launch needs; registered by callers that know them, else one
+        # .tolist() per offset tensor (the reference syncs once per scene, sampling.py:15-18)
+        sizes = C.scene_sizes(C.host_offset(offset))
+        m = C.host_offset(new_offset)[-1]
+        n_max = max(sizes) if sizes else 0
+        idx = torch.empty((m,), dtype=torch.int32, device=xyz.device)
+        if m == 0:
+            return idx
+        tmp = None
+        if n_max > 131072:  # beyond the register-resident capacity the kernel streams through tmp
+            tmp = torch.empty((xyz.shape[0],), dtype=torch.float32, device=xyz.device)
+        with torch.cuda.device(xyz.device):
+            rc = _lib.load().pob_farthest_point_sampling(b, n_max, _lib.ptr(xyz), _lib.ptr(offset),
+                                                         _lib.ptr(new_offset), _lib.ptr(tmp), _lib.ptr(idx), 0,
+                                                         _lib.current_stream(xyz.device))
+        _lib.check(rc, "pob_farthest_point_sampling")
+        ctx.mark_non_differentiable(idx)
+        return idx
+
+
+farthest_point_sampling = FarthestPointSampling.apply

@@ -1,0 +1,66 @@
+"""Generate the golden fixtures under tests/golden/ by running the REFERENCE's own Python code.
+
+Run here (needs /root/reference; never on the GPU box):   python tests/golden/make_golden.py
+
+The reference's ``libs/pointops/functions`` wrappers, ``PointTransformerSeg`` and recognizers are
+imported unmodified (oracle/ref_glue.py) over a ``pointops._C`` stub that calls the literal C
+restatement of the CUDA kernels (oracle/oracle_c.c), which is itself pinned bit-for-bit against
+the compiled reference kernels on the GPU box (tests/test_gpu_reference_ext.py).
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_glue  # noqa: E402
+from pointcloudpdf_b200 import synthetic as S  # noqa: E402
+
+
+def ops_small(R):
+    g = torch.Generator().manual_seed(2024)
+    sizes = [300, 5, 120]
+    xyz = torch.rand(sum(sizes), 3, generator=g) * torch.tensor([3.0, 2.0, 1.5])
+    offset = torch.tensor([300, 305, 425], dtype=torch.int32)
+    new_offset = torch.tensor([75, 76, 106], dtype=torch.int32)
+    feat = torch.randn(425, 8, generator=g)
+    feat2 = torch.randn(425, 8, generator=g)
+    pos = torch.randn(425, 16, 8, generator=g)
+    w = torch.randn(425, 16, 2, generator=g)
+    po = R.pointops
+    G = dict(xyz=xyz, offset=offset, new_offset=new_offset, feat=feat, feat2=feat2, pos=pos, w=w)
+    G["knn_idx"], G["knn_dist"] = po.knn_query(16, xyz, offset)
+    G["fps_idx"] = po.farthest_point_sampling(xyz, offset, new_offset)
+    G["grouped_xyz"] = po.grouping(G["knn_idx"], feat, xyz, xyz, with_xyz=True)
+    n_p = xyz[G["fps_idx"].long()].contiguous()
+    G["cross_grouped"], G["cross_idx"] = po.knn_query_and_group(feat, xyz, offset, n_p, new_offset, nsample=16,
+                                                                with_xyz=True)
+    G["interp"] = po.interpolation(n_p, xyz, feat[G["fps_idx"].long()].contiguous(), new_offset, offset)
+    safe = G["knn_idx"].clamp(min=0)
+    # aggregation / subtraction / grouping2 read out of bounds on -1 in the reference: use idx >= 0
+    G["aggregation"] = po.aggregation(feat, pos, w, safe)
+    G["subtraction"] = po.subtraction(feat, feat2, safe)
+    G["grouping2"] = po.grouping2(feat, safe)
+    G["qag"], G["qag_idx"] = po.query_and_group(8, xyz, xyz, feat, None, offset, offset, dilation=1)
+    torch.save(G, os.path.join(HERE, "ops_small.pt"))
+    return G
+
+
+def scores_small(R):
+    logits, conf, unknown, label = S.openset_logits(2000, 13, seed=2024)
+    rec = R.msp.MaxProbability(method="msp")
+    rec.model_hooks = {"backbone": {"forward_output": logits}}
+    msp = rec({})["score"]
+    rec2 = R.msp.MaxProbability(method="max_logits")
+    rec2.model_hooks = {"backbone": {"forward_output": logits}}
+    ml = rec2({})["score"]
+    torch.save(dict(logits=logits, conf=conf, msp=msp, ml=ml), os.path.join(HERE, "scores_small.pt"))
+
+
+if __name__ == "__main__":
+    with ref_glue.reference_modules() as R:
+        ops_small(R)
+        scores_small(R)
+    print("golden fixtures written to", HERE)
