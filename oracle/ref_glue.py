@@ -122,8 +122,12 @@ def reference_modules():
     for k in saved_modules:
         del sys.modules[k]
     saved_ctor = (torch.cuda.IntTensor, torch.cuda.FloatTensor)
+    saved_sqrt = torch.sqrt
     torch.cuda.IntTensor = _CpuTensorCtor(torch.int32)
     torch.cuda.FloatTensor = _CpuTensorCtor(torch.float32)
+    # The reference only ever calls torch.sqrt on CUDA tensors (IEEE-correct); torch's CPU float
+    # sqrt is an inexact SIMD routine, so give the wrappers the correctly rounded one here.
+    torch.sqrt = lambda x, *a, **k: O.sqrt_f32(x) if (x.dtype == torch.float32 and not a and not k) else saved_sqrt(x, *a, **k)
     try:
         fdir = os.path.join(REF_ROOT, "libs", "pointops", "functions")
         spec = importlib.util.spec_from_file_location("pointops", os.path.join(fdir, "__init__.py"),
@@ -176,6 +180,7 @@ def reference_modules():
         yield ns
     finally:
         torch.cuda.IntTensor, torch.cuda.FloatTensor = saved_ctor
+        torch.sqrt = saved_sqrt
         for k in [k for k in sys.modules if k == "pointops" or k.startswith("pointops.")
                   or k == "pointcept" or k.startswith("pointcept.")]:
             del sys.modules[k]
