@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- PTv1 openseg inference throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one synthetic S3DIS-Area-5-shaped room of 80 000
+points per GPU: Point Transformer v1 (Seg50, 13 classes, random-init, eval, f32) + the fused MSP
+open-set score -- BASELINE.json configs[1], "openseg-pt-v1-0-msp inference".  Rooms are
+independent, so N GPUs run N rooms with no data-path collective (weak scaling).
+
+Printed JSON (one line, rank 0):
+  value      whole-job points/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e        the same through the host-buffer API OpenSegPTv1.infer(): pinned-host -> device copy
+             of coord/feat/offset and device -> host read of score + prediction inside the timing
+  roofline   the kernel of ours with the largest share of the step, timed live with CUDA events
+             on the launching stream inside the timed region (achieved = algorithmic bytes / time)
+  kernels    the same accounting for every C-ABI entry point the step calls
+  cpu_baseline  the reference op sequence on the host cores (oracle port), bounded sample
+--impl reference times that CPU port alone (the reference has no CPU implementation of this path
+and its CUDA kernels are not a CPU baseline).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "ptv1_openseg_inference_points_per_sec"
+UNIT = "points/s"
+N_POINTS = 80_000
+NUM_CLASSES = 13
+IN_CHANNELS = 6
+L2_FLUSH_BYTES = 256 << 20  # > 126 MB L2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--cpu-sample-points", type=int, default=8192)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--literal", action="store_true", help="reference op sequence (kNN per block, einsum)")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------- clocks sampling --
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU port --
+
+def cpu_port_points_per_sec(n_points: int, steps: int, warmup: int, threads: int):
+    """The reference's op sequence for the same workload on host cores: PTv1 Seg50 (literal path:
+    kNN in every block, gather k and v, einsum) over the oracle's brute-force operators + MSP.
+    This is the one place bench.py executes oracle/ (cpu_baseline / --impl reference)."""
+    from oracle import pointops_oracle as O
+    from pointcloudpdf_b200 import ptv1, synthetic as S
+    import types
+
+    torch.set_num_threads(threads)
+    shim = types.SimpleNamespace(
+        knn_query=lambda k, xyz, off, nx=None, noff=None: O.knn_query(k, xyz, off, nx, noff),
+        farthest_point_sampling=O.farthest_point_sampling, grouping=O.grouping, aggregation=O.aggregation,
+        knn_query_and_group=O.knn_query_and_group, interpolation=O.interpolation)
+    saved = ptv1.pointops
+    ptv1.pointops = shim
+    try:
+        torch.manual_seed(2024)
+        net = ptv1.PointTransformerSeg50(in_channels=IN_CHANNELS, num_classes=NUM_CLASSES).eval().set_fused(False)
+        batch = S.s3dis_batch([n_points], seed=2026)
+        times = []
+        with torch.no_grad():
+            for i in range(warmup + steps):
+                t0 = time.perf_counter()
+                logits = net(dict(coord=batch["coord"], feat=batch["feat"], offset=batch["offset"]),
+                             batch["offset"].tolist())
+                O.msp_score(logits)
+                if i >= warmup:
+                    times.append(time.perf_counter() - t0)
+    finally:
+        ptv1.pointops = saved
+    return n_points / statistics.median(times), statistics.median(times)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = args.cpu_sample_points
+    pps, sec = cpu_port_points_per_sec(n, max(1, args.steps), max(0, min(args.warmup, 1)), cores)
+    sample = f"one S3DIS-shaped room of {n} points per step (bounded sample of the 80000-point workload; " \
+             f"brute-force kNN/FPS are O(n^2), so points/s at 80000 would be lower)"
+    line = {"impl": "reference", "metric": METRIC, "value": pps, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "openseg-pt-v1-0-msp inference, PTv1-Seg50, S3DIS-shaped room", "points_per_step": n,
+                       "classes": NUM_CLASSES},
+            "cpu_baseline": {"value": pps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------- B200 arm --
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+    from pointcloudpdf_b200 import _lib, synthetic as S
+    from pointcloudpdf_b200.ptv1 import OpenSegPTv1
+    import pointcloudpdf_b200.pointops as pointops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    K, W = args.steps, max(args.warmup, 3)
+    torch.backends.cuda.matmul.allow_tf32 = False  # f32 means f32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(2024)
+    net = OpenSegPTv1(in_channels=IN_CHANNELS, num_classes=NUM_CLASSES, method="msp").to(dev).eval()
+    net.backbone.set_fused(not args.literal)
+
+    # one distinct room per rank and per step slot (weak scaling: every GPU does a full room)
+    n_rooms = min(K, 4)
+    rooms = [S.s3dis_batch([args.points], seed=2026 + 101 * rank + i) for i in range(n_rooms)]
+    host = [dict(coord=r["coord"].pin_memory(), feat=r["feat"].pin_memory(), offset=r["offset"].pin_memory()) for r in rooms]
+    resident = [dict(coord=r["coord"].to(dev), feat=r["feat"].to(dev), offset=r["offset"].to(dev)) for r in rooms]
+    off_host = [r["offset"].tolist() for r in rooms]
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        flush.zero_()                       # evict L2 between timed iterations
+        pointops.clear_caches()             # nothing computed in a previous step may be reused
+        with torch.no_grad():
+            return net(resident[i % n_rooms], off_host[i % n_rooms])["score"]
+
+    def step_e2e(i):
+        flush.zero_()
+        pointops.clear_caches()
+        h = host[i % n_rooms]
+        return net.infer(h["coord"], h["feat"], h["offset"], device=dev)
+
+    for i in range(W):
+        step_resident(i)
+        step_e2e(i)
+    barrier()
+
+    # ---- value: device-resident inputs, K steps, CUDA events, op-level events inside ----
+    launches0 = _lib.launch_count()
+    prof = _lib.OpProfile()
+    _lib.PROFILE = prof
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for i in range(K):
+            step_resident(i)
+        e1.record()
+        barrier()
+    _lib.PROFILE = None
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    ops = prof.summary()
+
+    # ---- e2e: host buffers in, host score out ----
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(K):
+        score, pred = step_e2e(i)
+    e3.record()
+    barrier()
+    e2e_ms_total = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
+
+    t = torch.tensor([ms_total, e2e_ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms_total = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        step_ms = ms_total / K
+        kernels = {}
+        for name, d in sorted(ops.items(), key=lambda kv: -kv[1]["ms"]):
+            per_call_ms = d["ms"] / d["calls"]
+            gbs = d["alg_bytes"] / d["calls"] / (per_call_ms * 1e-3) / 1e9 if per_call_ms > 0 else 0.0
+            kernels[name] = {"calls_per_step": d["calls"] / K, "ms_per_step": d["ms"] / K,
+                             "share_of_step": d["ms"] / ms_total, "alg_MB_per_call": d["alg_bytes"] / d["calls"] / 1e6,
+                             "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
+                             "alg_GFLOP_per_call": d["alg_flops"] / d["calls"] / 1e9}
+        top = next(iter(kernels)) if kernels else None
+        roof = None
+        if top:
+            kd = kernels[top]
+            roof = {"kernel": top, "bound": "hbm", "achieved": kd["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": kd["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                    "share_of_step": kd["share_of_step"], "avg_launch_ms": kd["ms_per_step"] / kd["calls_per_step"]}
+        h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+        d2h = score.numel() * score.element_size() + pred.numel() * pred.element_size()
+        line = {"metric": METRIC, "value": world * args.points * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "openseg-pt-v1-0-msp inference (BASELINE configs[1]): PTv1-Seg50 + fused MSP score, "
+                                       "one S3DIS-Area-5-shaped room per GPU per step",
+                           "points_per_step_per_gpu": args.points, "classes": NUM_CLASSES, "in_channels": IN_CHANNELS,
+                           "op_sequence": "literal (kNN per block, einsum)" if args.literal else
+                                          "one kNN per stage + fused aggregation kernel",
+                           "l2": "256 MiB memset between timed iterations (inside the timed region)",
+                           "parallelism": f"scene-sharded x{world}, no data-path collective"},
+                "e2e": {"value": world * args.points * K / (e2e_ms_total * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_total / K},
+                "gpu_launches": launches, "gpu_launches_per_step": launches / K,
+                "roofline": roof, "kernels": kernels, "clocks": clocks.summary()}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n = args.cpu_sample_points
+            pps, sec = cpu_port_points_per_sec(n, 1, 1, cores)
+            line["cpu_baseline"] = {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"one {n}-point S3DIS-shaped room, reference op sequence over the "
+                                              f"brute-force oracle operators, {sec:.2f} s per room (O(n^2): an "
+                                              f"80000-point room would be slower per point)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

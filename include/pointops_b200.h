@@ -38,6 +38,8 @@ typedef struct CUstream_st* cudaStream_t;
 
 /* ABI version; bumped on any signature change. */
 int pob_version(void);
+/* Kernels launched by this library in this process so far (monotonic; for bench accounting). */
+long long pob_kernel_launch_count(void);
 /* Human-readable text for a return code (cudaGetErrorString for CUDA codes). Host pointer. */
 const char* pob_error_string(int code);
 
@@ -103,7 +105,9 @@ int pob_subtraction_backward(int64_t n, int nsample, int c, const int* idx, cons
 /* ------------------------------------------------- vector-attention aggregation ----------
  * aggregation_{forward,backward}_cuda_launcher (src/aggregation/aggregation_cuda_kernel.h:14-15).
  * forward: output[n,c] = sum_s (input[idx[n,s],c] + position[n,s,c]) * weight[n,s,c % w_c]
- *          (output overwritten; the reference accumulates into a zeroed buffer).
+ *          (output overwritten; the reference accumulates into a zeroed buffer).  idx < 0 (a kNN
+ *          placeholder) contributes a zero input row, matching pointops.grouping; the reference
+ *          kernel reads out of bounds there.
  * backward: grad_input[idx[n,s],c] += g*w (accumulated; caller zeroes); grad_position = g*w and
  *           grad_weight[n,s,j] = sum_{c % w_c == j} g * (input + position) (both overwritten).  */
 int pob_aggregation_forward(int64_t n, int nsample, int c, int w_c, const float* input, const float* position,

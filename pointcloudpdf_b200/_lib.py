@@ -22,6 +22,7 @@ P, I, L, F, Z = c_void_p, c_int, c_int64, c_float, c_size_t
 # name -> (restype, argtypes); mirrors include/pointops_b200.h line by line
 SIGNATURES = {
     "pob_version": (I, []),
+    "pob_kernel_launch_count": (ctypes.c_longlong, []),
     "pob_error_string": (ctypes.c_char_p, [I]),
     "pob_knn_grid_workspace_bytes": (Z, [L, I, F]),
     "pob_knn_grid_build": (I, [L, I, P, P, F, P, Z, P]),
@@ -87,3 +88,49 @@ def ptr(t) -> c_void_p:
 def current_stream(device) -> c_void_p:
     import torch
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+# ---------------------------------------------------------------- op-level timing (bench.py) --
+class OpProfile:
+    """CUDA-event bracket around every C-ABI call, on the stream the kernels are launched on.
+    Off by default; bench.py switches it on for the timed region to attribute step time to
+    kernels and to compute achieved GB/s from the algorithmic bytes the wrappers report."""
+
+    def __init__(self):
+        self.records = []  # (name, start_event, end_event, alg_bytes, alg_flops)
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, s, e, nbytes, flops in self.records:
+            d = out.setdefault(name, dict(calls=0, ms=0.0, alg_bytes=0, alg_flops=0))
+            d["calls"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["alg_bytes"] += nbytes
+            d["alg_flops"] += flops
+        return out
+
+
+PROFILE = None  # set to an OpProfile() to record
+
+
+def run(name: str, *args, alg_bytes: int = 0, alg_flops: int = 0) -> None:
+    """Call entry point `name`, raise on a non-zero status.  The last positional argument is the
+    stream; when profiling, events are recorded on torch's current stream (the same one)."""
+    fn = getattr(load(), name)
+    prof = PROFILE
+    if prof is None:
+        rc = fn(*args)
+    else:
+        import torch
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        prof.records.append((name, s, e, int(alg_bytes), int(alg_flops)))
+    check(rc, name)
+
+
+def launch_count() -> int:
+    return int(load().pob_kernel_launch_count())

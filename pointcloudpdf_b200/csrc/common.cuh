@@ -18,6 +18,9 @@
 // status codes above the cudaError_t range for argument errors
 enum { POB_ERR_BAD_ARG = 10001, POB_ERR_WORKSPACE = 10002, POB_ERR_UNSUPPORTED = 10003 };
 
+// process-wide count of kernels launched by this library (bench.py's gpu_launches evidence)
+extern "C" void pob_count_launches(int n);
+
 namespace pob {
 
 constexpr unsigned FULL = 0xffffffffu;

@@ -214,6 +214,7 @@ static int launch_cluster(K kernel, int b, int C, cudaStream_t stream, const flo
     void* args_tmp[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&tmp, (void*)&idx};
     void* args[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&idx};
     POB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)kernel, pass_tmp ? args_tmp : args));
+    pob_count_launches(1);
     return 0;
 }
 

@@ -189,7 +189,8 @@ aggregation_fwd_kernel(int64_t n, int ns, RowTile t, int wvec, const float* __re
             for (int s = sub; s < ns; s += t.spar) {
                 const int64_t r = p * ns + s;
                 const int src = __ldg(idx + r);
-                const float4 a = ld4(in + ((int64_t)src * t.cvec + cv) * 4);
+                // idx < 0 (kNN placeholder) contributes a zero row, like pointops.grouping does
+                const float4 a = src >= 0 ? ld4(in + ((int64_t)src * t.cvec + cv) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const float4 b = ld4_stream(pos + (r * t.cvec + cv) * 4);
                 const float4 ww = ld4(w + (r * wvec + wv) * 4);
                 acc = f4_fma(f4_add(a, b), ww, acc);
@@ -227,11 +228,11 @@ aggregation_bwd_kernel(int64_t n, int ns, RowTile t, int wvec, const float* __re
                 if (live) {
                     const float4 g = ld4(gout + (p * t.cvec + cv) * 4);
                     const float4 ww = ld4(w + (r * wvec + wv) * 4);
-                    const float4 a = ld4(in + ((int64_t)src * t.cvec + cv) * 4);
+                    const float4 a = src >= 0 ? ld4(in + ((int64_t)src * t.cvec + cv) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                     const float4 b = ld4_stream(pos + (r * t.cvec + cv) * 4);
                     const float4 gwv = f4_mul(g, ww);
                     st4_stream(gpos + (r * t.cvec + cv) * 4, gwv);
-                    red4(gin + ((int64_t)src * t.cvec + cv) * 4, gwv);
+                    if (src >= 0) red4(gin + ((int64_t)src * t.cvec + cv) * 4, gwv);
                     gws = f4_fma(g, f4_add(a, b), gws);
                 }
             }
@@ -396,7 +397,9 @@ __global__ void aggregation_fwd_scalar_kernel(int64_t n, int ns, int c, int w_c,
         float acc = 0.f;
         for (int s = 0; s < ns; s++) {
             const int64_t r = p * ns + s;
-            acc = fmaf(__ldg(in + (int64_t)__ldg(idx + r) * c + ch) + pos[r * c + ch], __ldg(w + r * w_c + ch % w_c), acc);
+            const int src = __ldg(idx + r);
+            const float a = src >= 0 ? __ldg(in + (int64_t)src * c + ch) : 0.f;
+            acc = fmaf(a + pos[r * c + ch], __ldg(w + r * w_c + ch % w_c), acc);
         }
         out[e] = acc;
     }
@@ -414,11 +417,12 @@ __global__ void aggregation_bwd_scalar_kernel(int64_t n, int ns, int c, int w_c,
         const float g = gout[e];
         for (int s = 0; s < ns; s++) {
             const int64_t r = p * ns + s;
-            const int64_t ii = (int64_t)__ldg(idx + r) * c + ch;
+            const int src = __ldg(idx + r);
+            const int64_t ii = (int64_t)src * c + ch;
             const float wt = __ldg(w + r * w_c + ch % w_c);
-            atomicAdd(gin + ii, g * wt);
+            if (src >= 0) atomicAdd(gin + ii, g * wt);
             gpos[r * c + ch] = g * wt;
-            atomicAdd(gw + r * w_c + ch % w_c, g * (__ldg(in + ii) + pos[r * c + ch]));
+            atomicAdd(gw + r * w_c + ch % w_c, g * ((src >= 0 ? __ldg(in + ii) : 0.f) + pos[r * c + ch]));
         }
     }
 }
@@ -473,6 +477,7 @@ POB_API int pob_grouping_forward(int64_t m, int nsample, int c, const float* inp
         gather_rows_scalar_kernel<<<grid_for(rows * c, 256, 8), 256, 0, stream>>>(rows * c, nsample, c, 0, input,
                                                                                   nullptr, idx, output);
     }
+    pob_count_launches(1);
     POB_RETURN_LAST_ERROR();
 }
 
@@ -492,6 +497,7 @@ POB_API int pob_grouping_backward(int64_t m, int nsample, int c, const float* gr
         scatter_rows_scalar_kernel<<<grid_for(rows * c, 256, 8), 256, 0, stream>>>(rows * c, c, 1.f, grad_output, idx,
                                                                                    grad_input);
     }
+    pob_count_launches(1);
     POB_RETURN_LAST_ERROR();
 }
 
@@ -510,6 +516,7 @@ POB_API int pob_subtraction_forward(int64_t n, int nsample, int c, const float* 
         gather_rows_scalar_kernel<<<grid_for(rows * c, 256, 8), 256, 0, stream>>>(rows * c, nsample, c, 1, input2,
                                                                                   input1, idx, output);
     }
+    pob_count_launches(1);
     POB_RETURN_LAST_ERROR();
 }
 
@@ -532,6 +539,7 @@ POB_API int pob_subtraction_backward(int64_t n, int nsample, int c, const int* i
         scatter_rows_scalar_kernel<<<grid_for(rows * c, 256, 8), 256, 0, stream>>>(rows * c, c, -1.f, grad_output, idx,
                                                                                    grad_input2);
     }
+    pob_count_launches(2);
     POB_RETURN_LAST_ERROR();
 }
 
@@ -561,6 +569,7 @@ POB_API int pob_aggregation_forward(int64_t n, int nsample, int c, int w_c, cons
         aggregation_fwd_scalar_kernel<<<grid_for(n * c, 256, 8), 256, 0, stream>>>(n, nsample, c, w_c, input, position,
                                                                                    weight, idx, output);
     }
+    pob_count_launches(1);
     POB_RETURN_LAST_ERROR();
 }
 
@@ -586,6 +595,7 @@ POB_API int pob_aggregation_backward(int64_t n, int nsample, int c, int w_c, con
         aggregation_bwd_scalar_kernel<<<grid_for(n * c, 256, 8), 256, 0, stream>>>(
             n, nsample, c, w_c, input, position, weight, idx, grad_output, grad_input, grad_position, grad_weight);
     }
+    pob_count_launches(1);
     POB_RETURN_LAST_ERROR();
 }
 
@@ -603,6 +613,7 @@ POB_API int pob_interpolation_forward(int64_t n, int c, int k, const float* inpu
     } else {
         interpolation_fwd_scalar_kernel<<<grid_for(n * c, 256, 8), 256, 0, stream>>>(n, c, k, input, idx, weight, output);
     }
+    pob_count_launches(1);
     POB_RETURN_LAST_ERROR();
 }
 
@@ -621,6 +632,7 @@ POB_API int pob_interpolation_backward(int64_t n, int c, int k, const float* gra
         interpolation_bwd_scalar_kernel<<<grid_for(n * c, 256, 8), 256, 0, stream>>>(n, c, k, grad_output, idx, weight,
                                                                                      grad_input);
     }
+    pob_count_launches(1);
     POB_RETURN_LAST_ERROR();
 }
 
@@ -642,6 +654,7 @@ POB_API int pob_group_xyz_forward(int64_t m, int nsample, int c, int with_xyz, c
     else
         group_xyz_fwd_kernel<__nv_bfloat16><<<grid, GATHER_THREADS, 0, stream>>>(
             m, nsample, c, with_xyz, (const __nv_bfloat16*)feat, xyz, new_xyz, idx, output);
+    pob_count_launches(1);
     POB_RETURN_LAST_ERROR();
 }
 
@@ -654,5 +667,6 @@ POB_API int pob_group_xyz_backward(int64_t m, int nsample, int c, int with_xyz, 
     if (!grad_output || !idx || !grad_feat) return POB_ERR_BAD_ARG;
     group_xyz_bwd_kernel<<<warp_grid(m), GATHER_THREADS, 0, stream>>>(m, nsample, c, with_xyz ? 3 : 0, grad_output, idx,
                                                                       grad_feat);
+    pob_count_launches(1);
     POB_RETURN_LAST_ERROR();
 }

@@ -493,6 +493,7 @@ POB_API int pob_knn_grid_build(int64_t n, int b, const float* xyz, const int* of
     }
     scan_apply_kernel<<<(unsigned)ntiles, 512, 0, stream>>>(cnt, cap1, tiles, start);
     if (n > 0) grid_scatter_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(n, xyz, pcell, cnt, start, sorted);
+    pob_count_launches((n > 0 ? 6 : 3) + (ntiles > 1 ? 2 : 0));
     POB_RETURN_LAST_ERROR();
 }
 
@@ -508,6 +509,7 @@ static int knn_launch(int64_t m, int k, int b, const float* xyz, const float* ne
     else if (k <= 128) POB_KNN_LAUNCH(4);
     else POB_KNN_LAUNCH(8);
 #undef POB_KNN_LAUNCH
+    pob_count_launches(1);
     POB_RETURN_LAST_ERROR();
 }
 
@@ -561,6 +563,7 @@ POB_API int pob_knn_query_bruteforce(int64_t m, int nsample, int b, const float*
     if (m == 0) return 0;
     SceneGrid* scenes = (SceneGrid*)workspace;
     scene_table_kernel<<<(unsigned)ceil_div(b, 128), 128, 0, stream>>>(offset, b, scenes);
+    pob_count_launches(1);
     return knn_launch(m, nsample, b, xyz, new_xyz, new_offset, scenes, nullptr, nullptr, idx, dist, nullptr, take_sqrt,
                       1, stream);
 }

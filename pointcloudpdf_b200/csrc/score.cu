@@ -238,5 +238,6 @@ POB_API int pob_score_fused(int64_t n, int K, int b, const float* logits, const 
         if (ml_norm)
             score_normalise_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(n, b, offset, max_logit, scene_out, ml_norm);
     }
+    pob_count_launches(1 + (want_stats ? 2 + (ml_norm ? 1 : 0) : 0));
     POB_RETURN_LAST_ERROR();
 }

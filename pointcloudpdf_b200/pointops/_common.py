@@ -122,9 +122,8 @@ class NeighbourGrid:
         self.n, self.b, self.cell_pts = int(xyz.shape[0]), int(offset.numel()), float(cell_pts)
         nbytes = lib.pob_knn_grid_workspace_bytes(self.n, self.b, self.cell_pts)
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=xyz.device)
-        rc = lib.pob_knn_grid_build(self.n, self.b, _lib.ptr(xyz), _lib.ptr(offset), self.cell_pts,
-                                    _lib.ptr(self.workspace), nbytes, _lib.current_stream(xyz.device))
-        _lib.check(rc, "pob_knn_grid_build")
+        _lib.run("pob_knn_grid_build", self.n, self.b, _lib.ptr(xyz), _lib.ptr(offset), self.cell_pts,
+                 _lib.ptr(self.workspace), nbytes, _lib.current_stream(xyz.device), alg_bytes=28 * self.n)
 
     def query(self, nsample: int, new_xyz: torch.Tensor, new_offset: torch.Tensor, want_dist=True, want_weight=False):
         lib = _lib.load()
@@ -133,10 +132,12 @@ class NeighbourGrid:
         idx = torch.empty((m, nsample), dtype=torch.int32, device=dev)
         dist = torch.empty((m, nsample), dtype=torch.float32, device=dev) if want_dist else None
         weight = torch.empty((m, nsample), dtype=torch.float32, device=dev) if want_weight else None
-        rc = lib.pob_knn_grid_query(m, int(nsample), self.n, self.b, _lib.ptr(self.xyz), _lib.ptr(new_xyz),
-                                    _lib.ptr(new_offset), self.cell_pts, _lib.ptr(self.workspace), _lib.ptr(idx),
-                                    _lib.ptr(dist), _lib.ptr(weight), 1, _lib.current_stream(dev))
-        _lib.check(rc, "pob_knn_grid_query")
+        outs = 1 + (dist is not None) + (weight is not None)
+        _lib.run("pob_knn_grid_query", m, int(nsample), self.n, self.b, _lib.ptr(self.xyz), _lib.ptr(new_xyz),
+                 _lib.ptr(new_offset), self.cell_pts, _lib.ptr(self.workspace), _lib.ptr(idx), _lib.ptr(dist),
+                 _lib.ptr(weight), 1, _lib.current_stream(dev),
+                 alg_bytes=12 * self.n + 12 * m + 4 * outs * nsample * m,
+                 alg_flops=8 * m * max(self.n // max(self.b, 1), 1))             # brute-force equivalent
         return idx, dist, weight
 
 

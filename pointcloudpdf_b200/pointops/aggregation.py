@@ -26,10 +26,9 @@ class Aggregation(Function):
             raise ValueError("aggregation: weight channels must divide feature channels")
         output = torch.empty((n, c), dtype=torch.float32, device=input.device)
         with torch.cuda.device(input.device):
-            rc = _lib.load().pob_aggregation_forward(n, nsample, c, w_c, _lib.ptr(input), _lib.ptr(position),
-                                                     _lib.ptr(weight), _lib.ptr(idx), _lib.ptr(output),
-                                                     _lib.current_stream(input.device))
-        _lib.check(rc, "pob_aggregation_forward")
+            _lib.run("pob_aggregation_forward", n, nsample, c, w_c, _lib.ptr(input), _lib.ptr(position),
+                     _lib.ptr(weight), _lib.ptr(idx), _lib.ptr(output), _lib.current_stream(input.device),
+                     alg_bytes=4 * (input.shape[0] * c + n * nsample * c + n * nsample * w_c + n * nsample + n * c))
         ctx.save_for_backward(input, position, weight, idx)
         return output
 
@@ -44,11 +43,11 @@ class Aggregation(Function):
         grad_position = torch.empty_like(position)
         grad_weight = torch.empty_like(weight)
         with torch.cuda.device(dev):
-            rc = _lib.load().pob_aggregation_backward(n, nsample, c, w_c, _lib.ptr(input), _lib.ptr(position),
-                                                      _lib.ptr(weight), _lib.ptr(idx), _lib.ptr(grad_output),
-                                                      _lib.ptr(grad_input), _lib.ptr(grad_position),
-                                                      _lib.ptr(grad_weight), _lib.current_stream(dev))
-        _lib.check(rc, "pob_aggregation_backward")
+            fwd_in = input.shape[0] * c + n * nsample * c + n * nsample * w_c + n * nsample
+            _lib.run("pob_aggregation_backward", n, nsample, c, w_c, _lib.ptr(input), _lib.ptr(position),
+                     _lib.ptr(weight), _lib.ptr(idx), _lib.ptr(grad_output), _lib.ptr(grad_input),
+                     _lib.ptr(grad_position), _lib.ptr(grad_weight), _lib.current_stream(dev),
+                     alg_bytes=4 * (fwd_in + n * c + input.shape[0] * c + n * nsample * c + n * nsample * w_c))
         return grad_input, grad_position, grad_weight, None
 
 

@@ -23,9 +23,8 @@ class Grouping(Function):
         n, c = input.shape
         output = torch.empty((m, nsample, c), dtype=torch.float32, device=input.device)
         with torch.cuda.device(input.device):
-            rc = _lib.load().pob_grouping_forward(m, nsample, c, _lib.ptr(input), _lib.ptr(idx), _lib.ptr(output),
-                                                  _lib.current_stream(input.device))
-        _lib.check(rc, "pob_grouping_forward")
+            _lib.run("pob_grouping_forward", m, nsample, c, _lib.ptr(input), _lib.ptr(idx), _lib.ptr(output),
+                     _lib.current_stream(input.device), alg_bytes=4 * (n * c + m * nsample + m * nsample * c))
         ctx.n = n
         ctx.save_for_backward(idx)
         return output
@@ -37,9 +36,9 @@ class Grouping(Function):
         m, nsample, c = grad_output.shape
         grad_input = torch.zeros((ctx.n, c), dtype=torch.float32, device=grad_output.device)
         with torch.cuda.device(grad_output.device):
-            rc = _lib.load().pob_grouping_backward(m, nsample, c, _lib.ptr(grad_output), _lib.ptr(idx),
-                                                   _lib.ptr(grad_input), _lib.current_stream(grad_output.device))
-        _lib.check(rc, "pob_grouping_backward")
+            _lib.run("pob_grouping_backward", m, nsample, c, _lib.ptr(grad_output), _lib.ptr(idx),
+                     _lib.ptr(grad_input), _lib.current_stream(grad_output.device),
+                     alg_bytes=4 * (ctx.n * c + m * nsample + m * nsample * c))
         return grad_input, None
 
 
@@ -56,10 +55,11 @@ class _GroupXYZ(Function):
         width = c + (3 if with_xyz else 0)
         out = torch.empty((m, nsample, width), dtype=torch.float32, device=feat.device)
         with torch.cuda.device(feat.device):
-            rc = _lib.load().pob_group_xyz_forward(m, nsample, c, 1 if with_xyz else 0, _lib.ptr(feat),
-                                                   _DTYPE_CODE[feat.dtype], _lib.ptr(xyz), _lib.ptr(new_xyz),
-                                                   _lib.ptr(idx), _lib.ptr(out), _lib.current_stream(feat.device))
-        _lib.check(rc, "pob_group_xyz_forward")
+            x3 = 3 if with_xyz else 0
+            _lib.run("pob_group_xyz_forward", m, nsample, c, 1 if with_xyz else 0, _lib.ptr(feat),
+                     _DTYPE_CODE[feat.dtype], _lib.ptr(xyz), _lib.ptr(new_xyz), _lib.ptr(idx), _lib.ptr(out),
+                     _lib.current_stream(feat.device),
+                     alg_bytes=feat.element_size() * n * c + 4 * (x3 * n + x3 * m + m * nsample + m * nsample * width))
         ctx.shape = (n, c, bool(with_xyz), feat.dtype)
         ctx.save_for_backward(idx)
         return out
@@ -72,10 +72,9 @@ class _GroupXYZ(Function):
         m, nsample = idx.shape
         grad_feat = torch.zeros((n, c), dtype=torch.float32, device=grad_out.device)
         with torch.cuda.device(grad_out.device):
-            rc = _lib.load().pob_group_xyz_backward(m, nsample, c, 1 if with_xyz else 0, _lib.ptr(grad_out),
-                                                    _lib.ptr(idx), _lib.ptr(grad_feat),
-                                                    _lib.current_stream(grad_out.device))
-        _lib.check(rc, "pob_group_xyz_backward")
+            _lib.run("pob_group_xyz_backward", m, nsample, c, 1 if with_xyz else 0, _lib.ptr(grad_out),
+                     _lib.ptr(idx), _lib.ptr(grad_feat), _lib.current_stream(grad_out.device),
+                     alg_bytes=4 * (n * c + m * nsample + m * nsample * (c + (3 if with_xyz else 0))))
         return grad_feat.to(dtype), None, None, None, None
 
 

@@ -17,9 +17,8 @@ class _InterpolateRows(Function):
         m, c = input.shape
         output = torch.empty((n, c), dtype=torch.float32, device=input.device)
         with torch.cuda.device(input.device):
-            rc = _lib.load().pob_interpolation_forward(n, c, k, _lib.ptr(input), _lib.ptr(idx), _lib.ptr(weight),
-                                                       _lib.ptr(output), _lib.current_stream(input.device))
-        _lib.check(rc, "pob_interpolation_forward")
+            _lib.run("pob_interpolation_forward", n, c, k, _lib.ptr(input), _lib.ptr(idx), _lib.ptr(weight),
+                     _lib.ptr(output), _lib.current_stream(input.device), alg_bytes=4 * (m * c + 2 * n * k + n * c))
         ctx.m = m
         ctx.save_for_backward(idx, weight)
         return output
@@ -32,10 +31,9 @@ class _InterpolateRows(Function):
         k = idx.shape[1]
         grad_input = torch.zeros((ctx.m, c), dtype=torch.float32, device=grad_output.device)
         with torch.cuda.device(grad_output.device):
-            rc = _lib.load().pob_interpolation_backward(n, c, k, _lib.ptr(grad_output), _lib.ptr(idx),
-                                                        _lib.ptr(weight), _lib.ptr(grad_input),
-                                                        _lib.current_stream(grad_output.device))
-        _lib.check(rc, "pob_interpolation_backward")
+            _lib.run("pob_interpolation_backward", n, c, k, _lib.ptr(grad_output), _lib.ptr(idx), _lib.ptr(weight),
+                     _lib.ptr(grad_input), _lib.current_stream(grad_output.device),
+                     alg_bytes=4 * (ctx.m * c + 2 * n * k + n * c))
         return grad_input, None, None
 
 
@@ -79,9 +77,8 @@ class Interpolation(Function):
         n, c, m = new_xyz.shape[0], input.shape[1], input.shape[0]
         output = torch.empty((n, c), dtype=torch.float32, device=input.device)
         with torch.cuda.device(input.device):
-            rc = _lib.load().pob_interpolation_forward(n, c, int(k), _lib.ptr(input), _lib.ptr(idx), _lib.ptr(weight),
-                                                       _lib.ptr(output), _lib.current_stream(input.device))
-        _lib.check(rc, "pob_interpolation_forward")
+            _lib.run("pob_interpolation_forward", n, c, int(k), _lib.ptr(input), _lib.ptr(idx), _lib.ptr(weight),
+                     _lib.ptr(output), _lib.current_stream(input.device), alg_bytes=4 * (m * c + 2 * n * int(k) + n * c))
         ctx.m, ctx.k = m, int(k)
         ctx.save_for_backward(idx, weight)
         return output
@@ -93,10 +90,9 @@ class Interpolation(Function):
         n, c = grad_output.shape
         grad_input = torch.zeros((ctx.m, c), dtype=torch.float32, device=grad_output.device)
         with torch.cuda.device(grad_output.device):
-            rc = _lib.load().pob_interpolation_backward(n, c, ctx.k, _lib.ptr(grad_output), _lib.ptr(idx),
-                                                        _lib.ptr(weight), _lib.ptr(grad_input),
-                                                        _lib.current_stream(grad_output.device))
-        _lib.check(rc, "pob_interpolation_backward")
+            _lib.run("pob_interpolation_backward", n, c, ctx.k, _lib.ptr(grad_output), _lib.ptr(idx), _lib.ptr(weight),
+                     _lib.ptr(grad_input), _lib.current_stream(grad_output.device),
+                     alg_bytes=4 * (ctx.m * c + 2 * n * ctx.k + n * c))
         return None, None, grad_input, None, None, None
 
 

@@ -33,10 +33,11 @@ class FarthestPointSampling(Function):
         if n_max > 131072:  # beyond the register-resident capacity the kernel streams through tmp
             tmp = torch.empty((xyz.shape[0],), dtype=torch.float32, device=xyz.device)
         with torch.cuda.device(xyz.device):
-            rc = _lib.load().pob_farthest_point_sampling(b, n_max, _lib.ptr(xyz), _lib.ptr(offset),
-                                                         _lib.ptr(new_offset), _lib.ptr(tmp), _lib.ptr(idx), 0,
-                                                         _lib.current_stream(xyz.device))
-        _lib.check(rc, "pob_farthest_point_sampling")
+            noff = C.host_offset(new_offset)
+            flops = sum(10 * max(mb - 1, 0) * nb for nb, mb in zip(sizes, C.scene_sizes(noff)))
+            _lib.run("pob_farthest_point_sampling", b, n_max, _lib.ptr(xyz), _lib.ptr(offset), _lib.ptr(new_offset),
+                     _lib.ptr(tmp), _lib.ptr(idx), 0, _lib.current_stream(xyz.device),
+                     alg_bytes=12 * xyz.shape[0] + 4 * m, alg_flops=flops)
         ctx.mark_non_differentiable(idx)
         return idx
 

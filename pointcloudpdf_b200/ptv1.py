@@ -1,0 +1,332 @@
+"""Point Transformer v1 (Seg26/38/50) on the B200 point operators.
+
+Host-side mirror of the reference backbone ``pointcept/models/point_transformer/
+point_transformer_seg.py`` (PointTransformerLayer :22-81, TransitionDown :84-122, TransitionUp
+:125-171, Bottleneck :174-195, PointTransformerSeg :198-306) and of the PDF U-decoder
+``pointcept/recognizers/recognizer_model/pt_v1.py:8-44``.  The reference model files run
+unmodified on ``import pointops`` from this repo; this mirror exists because they cannot travel
+to the GPU box, and because the caller is where the remaining waste sits:
+
+  * identical module tree, parameter names, construction order and maths -> ``state_dict``s are
+    interchangeable and, under the same seed, identical (tests/test_cpu_ptv1.py);
+  * one kNN per stage instead of one per block (the cloud does not change inside a stage;
+    the reference recomputes it 18x per forward, :51) -- same indices, bit for bit;
+  * vector attention ``einsum(x_v[idx] + p_r, w)`` runs as the fused ``pointops.aggregation``
+    kernel (mathematically identical), so the gathered values are never stored;
+  * ``LayerNorm1d`` (= BatchNorm1d over a transposed copy, point_transformer/utils.py:7-14)
+    normalises the (n*ns, c) view directly: same statistics, no transposes;
+  * no ``.item()`` / per-scene python loops on device tensors (:99-103, :152-164): stage sizes
+    come from the host copy of ``offset``.
+
+``fused=False`` reproduces the reference's op sequence literally (gather both k and v, einsum),
+which the parity tests compare against.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import pointops
+from .pointops import _common as C
+
+
+class Cloud:
+    """One resolution level: coordinates, features, cumulative offsets (device + host copy) and
+    the self-kNN index shared by every block of the level."""
+
+    __slots__ = ("p", "x", "o", "o_host", "_knn")
+
+    def __init__(self, p, x, o, o_host):
+        self.p, self.x, self.o, self.o_host = p, x, o, list(o_host)
+        self._knn = {}
+
+    def with_feat(self, x) -> "Cloud":
+        c = Cloud(self.p, x, self.o, self.o_host)
+        c._knn = self._knn
+        return c
+
+    def knn(self, nsample: int) -> torch.Tensor:
+        idx = self._knn.get(nsample)
+        if idx is None:
+            idx, _ = pointops.knn_query(nsample, self.p, self.o)
+            self._knn[nsample] = idx
+        return idx
+
+
+class LayerNorm1d(nn.BatchNorm1d):
+    """BatchNorm over the channel axis of (n, ns, c); same parameters/buffers as the reference's
+    transposing subclass (point_transformer/utils.py:7-14), applied on the flattened view."""
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        if input.dim() != 3:
+            return super().forward(input)
+        n, ns, c = input.shape
+        return super().forward(input.reshape(n * ns, c)).view(n, ns, c)
+
+
+class PointTransformerLayer(nn.Module):
+    def __init__(self, in_planes, out_planes, share_planes=8, nsample=16):
+        super().__init__()
+        self.mid_planes = mid_planes = out_planes // 1
+        self.out_planes = out_planes
+        self.share_planes = share_planes
+        self.nsample = nsample
+        self.linear_q = nn.Linear(in_planes, mid_planes)
+        self.linear_k = nn.Linear(in_planes, mid_planes)
+        self.linear_v = nn.Linear(in_planes, out_planes)
+        self.linear_p = nn.Sequential(nn.Linear(3, 3), LayerNorm1d(3), nn.ReLU(inplace=True), nn.Linear(3, out_planes))
+        self.linear_w = nn.Sequential(
+            LayerNorm1d(mid_planes), nn.ReLU(inplace=True), nn.Linear(mid_planes, out_planes // share_planes),
+            LayerNorm1d(out_planes // share_planes), nn.ReLU(inplace=True),
+            nn.Linear(out_planes // share_planes, out_planes // share_planes))
+        self.softmax = nn.Softmax(dim=1)
+        self.fused = True
+
+    def forward(self, cloud: Cloud) -> torch.Tensor:
+        p, x, o = cloud.p, cloud.x, cloud.o
+        x_q, x_k, x_v = self.linear_q(x), self.linear_k(x), self.linear_v(x)
+        if self.fused:
+            idx = cloud.knn(self.nsample)
+        else:  # the reference's literal sequence: kNN inside every layer
+            idx, _ = pointops.knn_query(self.nsample, p, o)
+        g = pointops.grouping(idx, x_k, p, p, with_xyz=True)  # (n, ns, 3 + c)
+        p_r, x_kg = g[:, :, 0:3], g[:, :, 3:]
+        p_r = self.linear_p(p_r)                                # (n, ns, out)
+        n, ns, _ = p_r.shape
+        # the reference reduces p_r over "(i j) -> j" with j = mid_planes; i == 1 here: the identity
+        p_mid = p_r if self.out_planes == self.mid_planes else p_r.view(n, ns, -1, self.mid_planes).sum(2)
+        r_qk = x_kg - x_q.unsqueeze(1) + p_mid
+        w = self.softmax(self.linear_w(r_qk))                   # (n, ns, out // share), softmax over neighbours
+        if self.fused:
+            return pointops.aggregation(x_v.float().contiguous(), p_r.float().contiguous(), w.float().contiguous(), idx)
+        x_vg = pointops.grouping(idx, x_v, p, p, with_xyz=False)
+        s = self.share_planes
+        out = torch.einsum("ntsi,nti->nsi", (x_vg + p_r).view(n, ns, s, self.out_planes // s), w)
+        return out.reshape(n, self.out_planes)
+
+
+class TransitionDown(nn.Module):
+    def __init__(self, in_planes, out_planes, stride=1, nsample=16):
+        super().__init__()
+        self.stride, self.nsample = stride, nsample
+        if stride != 1:
+            self.linear = nn.Linear(3 + in_planes, out_planes, bias=False)
+            self.pool = nn.MaxPool1d(nsample)
+        else:
+            self.linear = nn.Linear(in_planes, out_planes, bias=False)
+        self.bn = nn.BatchNorm1d(out_planes)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, cloud: Cloud) -> Cloud:
+        if self.stride == 1:
+            return cloud.with_feat(self.relu(self.bn(self.linear(cloud.x))))
+        p, x, o = cloud.p, cloud.x, cloud.o
+        # per-scene sample counts n_b // stride, cumulative (point_transformer_seg.py:99-103), on the host
+        sizes = C.scene_sizes(cloud.o_host)
+        n_o_host, acc = [], 0
+        for s in sizes:
+            acc += s // self.stride
+            n_o_host.append(acc)
+        n_o = torch.tensor(n_o_host, dtype=torch.int32).to(p.device, non_blocking=True)
+        C.register_host_offset(n_o, n_o_host)
+        C.register_host_offset(o, cloud.o_host)
+        idx = pointops.farthest_point_sampling(p, o, n_o)          # (m)
+        n_p = p[idx.long(), :]                                     # (m, 3)
+        g, _ = pointops.knn_query_and_group(x, p, offset=o, new_xyz=n_p, new_offset=n_o, nsample=self.nsample,
+                                            with_xyz=True)        # (m, ns, 3 + c)
+        m, ns, w = g.shape
+        y = self.relu(self.bn(self.linear(g).view(m * ns, -1)))    # BN over (m, ns) per channel, no transpose
+        y = y.view(m, ns, -1).max(dim=1)[0]                        # MaxPool1d(nsample)
+        return Cloud(n_p, y, n_o, n_o_host)
+
+
+class TransitionUp(nn.Module):
+    def __init__(self, in_planes, out_planes=None):
+        super().__init__()
+        if out_planes is None:
+            self.linear1 = nn.Sequential(nn.Linear(2 * in_planes, in_planes), nn.BatchNorm1d(in_planes),
+                                         nn.ReLU(inplace=True))
+            self.linear2 = nn.Sequential(nn.Linear(in_planes, in_planes), nn.ReLU(inplace=True))
+        else:
+            self.linear1 = nn.Sequential(nn.Linear(out_planes, out_planes), nn.BatchNorm1d(out_planes),
+                                         nn.ReLU(inplace=True))
+            self.linear2 = nn.Sequential(nn.Linear(in_planes, out_planes), nn.BatchNorm1d(out_planes),
+                                         nn.ReLU(inplace=True))
+
+    def forward(self, fine: Cloud, coarse: Optional[Cloud] = None) -> torch.Tensor:
+        if coarse is None:
+            # head: concatenate every point with its scene's mean feature (:152-164), segmented
+            x = fine.x
+            sizes = C.scene_sizes(fine.o_host)
+            b = len(sizes)
+            if b == 1:
+                mean = x.sum(0, keepdim=True) / sizes[0]
+                tiled = self.linear2(mean).expand(x.shape[0], -1)
+            else:
+                counts = torch.tensor(sizes, dtype=torch.int64).to(x.device, non_blocking=True)
+                batch = torch.repeat_interleave(torch.arange(b, device=x.device), counts, output_size=x.shape[0])
+                sums = torch.zeros((b, x.shape[1]), dtype=x.dtype, device=x.device).index_add_(0, batch, x)
+                tiled = self.linear2(sums / counts.to(x.dtype).unsqueeze(1))[batch]
+            return self.linear1(torch.cat((x, tiled), 1))
+        up = pointops.interpolation(coarse.p, fine.p, self.linear2(coarse.x), coarse.o, fine.o)
+        return self.linear1(fine.x) + up
+
+
+class Bottleneck(nn.Module):
+    expansion = 1
+
+    def __init__(self, in_planes, planes, share_planes=8, nsample=16):
+        super().__init__()
+        self.linear1 = nn.Linear(in_planes, planes, bias=False)
+        self.bn1 = nn.BatchNorm1d(planes)
+        self.transformer = PointTransformerLayer(planes, planes, share_planes, nsample)
+        self.bn2 = nn.BatchNorm1d(planes)
+        self.linear3 = nn.Linear(planes, planes * self.expansion, bias=False)
+        self.bn3 = nn.BatchNorm1d(planes * self.expansion)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, cloud: Cloud) -> Cloud:
+        identity = cloud.x
+        x = self.relu(self.bn1(self.linear1(cloud.x)))
+        x = self.relu(self.bn2(self.transformer(cloud.with_feat(x))))
+        x = self.bn3(self.linear3(x))
+        x = self.relu(x + identity)
+        return cloud.with_feat(x)
+
+
+class PointTransformerSeg(nn.Module):
+    """Encoder-decoder of point_transformer_seg.py:198-306; ``forward(data_dict)`` takes the
+    reference's dict (coord, feat, offset) and returns per-point logits."""
+
+    def __init__(self, block, blocks, in_channels=6, num_classes=13):
+        super().__init__()
+        self.in_channels = in_channels
+        self.in_planes, planes = in_channels, [32, 64, 128, 256, 512]
+        share_planes = 8
+        stride, nsample = [1, 4, 4, 4, 4], [8, 16, 16, 16, 16]
+        for i in range(5):
+            setattr(self, f"enc{i + 1}", self._make_enc(block, planes[i], blocks[i], share_planes, stride[i], nsample[i]))
+        for i in (4, 3, 2, 1, 0):
+            setattr(self, f"dec{i + 1}", self._make_dec(block, planes[i], 1, share_planes, nsample[i], is_head=(i == 4)))
+        self.cls = nn.Sequential(nn.Linear(planes[0], planes[0]), nn.BatchNorm1d(planes[0]), nn.ReLU(inplace=True),
+                                 nn.Linear(planes[0], num_classes))
+        self.taps = None  # filled per forward: what the reference's ModelHook would capture
+
+    def _make_enc(self, block, planes, blocks, share_planes=8, stride=1, nsample=16):
+        layers = [TransitionDown(self.in_planes, planes * block.expansion, stride, nsample)]
+        self.in_planes = planes * block.expansion
+        for _ in range(blocks):
+            layers.append(block(self.in_planes, self.in_planes, share_planes, nsample=nsample))
+        return nn.Sequential(*layers)
+
+    def _make_dec(self, block, planes, blocks, share_planes=8, nsample=16, is_head=False):
+        layers = [TransitionUp(self.in_planes, None if is_head else planes * block.expansion)]
+        self.in_planes = planes * block.expansion
+        for _ in range(blocks):
+            layers.append(block(self.in_planes, self.in_planes, share_planes, nsample=nsample))
+        return nn.Sequential(*layers)
+
+    def set_fused(self, fused: bool) -> "PointTransformerSeg":
+        for m in self.modules():
+            if isinstance(m, PointTransformerLayer):
+                m.fused = bool(fused)
+        return self
+
+    def forward(self, data_dict, offset_host: Optional[Sequence[int]] = None):
+        p0, x0 = data_dict["coord"], data_dict["feat"]
+        o0 = data_dict["offset"].int()
+        if offset_host is None:
+            offset_host = C.host_offset(o0)
+        else:
+            C.register_host_offset(o0, offset_host)
+        c1 = self.enc1(Cloud(p0, x0, o0, offset_host))
+        c2 = self.enc2(c1)
+        c3 = self.enc3(c2)
+        c4 = self.enc4(c3)
+        c5 = self.enc5(c4)
+        d5 = self.dec5[1:](c5.with_feat(self.dec5[0](c5)))
+        d4 = self.dec4[1:](c4.with_feat(self.dec4[0](c4, d5)))
+        d3 = self.dec3[1:](c3.with_feat(self.dec3[0](c3, d4)))
+        d2 = self.dec2[1:](c2.with_feat(self.dec2[0](c2, d3)))
+        d1 = self.dec1[1:](c1.with_feat(self.dec1[0](c1, d2)))
+        self.taps = dict(enc=[c1, c2, c3, c4, c5], dec=[d1, d2, d3, d4, d5])
+        return self.cls(d1.x)
+
+
+class PointTransformerSeg26(PointTransformerSeg):
+    def __init__(self, **kwargs):
+        super().__init__(Bottleneck, [1, 1, 1, 1, 1], **kwargs)
+
+
+class PointTransformerSeg38(PointTransformerSeg):
+    def __init__(self, **kwargs):
+        super().__init__(Bottleneck, [1, 2, 2, 2, 2], **kwargs)
+
+
+class PointTransformerSeg50(PointTransformerSeg):
+    def __init__(self, **kwargs):
+        super().__init__(Bottleneck, [1, 2, 3, 5, 2], **kwargs)
+
+
+class PTRecognizer(nn.Module):
+    """PDF U-decoder (recognizers/recognizer_model/pt_v1.py:8-44): five TransitionUp over the
+    backbone's hooked encoder/decoder activations, then a confidence head -> conf (n, 1)."""
+
+    def __init__(self):
+        super().__init__()
+        planes = [32, 64, 128, 256, 512]
+        self.dec5 = TransitionUp(planes[4], planes[4])
+        self.dec4 = TransitionUp(planes[4], planes[3])
+        self.dec3 = TransitionUp(planes[3], planes[2])
+        self.dec2 = TransitionUp(planes[2], planes[1])
+        self.dec1 = TransitionUp(planes[1], planes[0])
+        self.confidence = nn.Sequential(nn.Linear(planes[0], planes[0]), nn.BatchNorm1d(planes[0]),
+                                        nn.ReLU(inplace=True), nn.Linear(planes[0], 1))
+
+    def forward(self, taps) -> torch.Tensor:
+        enc, dec = taps["enc"], taps["dec"]
+        c1, c2, c3, c4, c5 = enc
+        d1, d2, d3, d4, d5 = dec
+        r5 = self.dec5(d5, c5)                       # ([p5, x5_dec, o5], [p5, x5_enc, o5])
+        r4 = self.dec4(d4, c5.with_feat(r5))
+        r3 = self.dec3(d3, c4.with_feat(r4))
+        r2 = self.dec2(d2, c3.with_feat(r3))
+        r1 = self.dec1(d1, c2.with_feat(r2))
+        return self.confidence(r1)
+
+
+class OpenSegPTv1(nn.Module):
+    """What an ``openseg-pt-v1-0-{msp,ml,pointpdf}`` evaluation step computes per batch
+    (hooks/evaluator.py:39-72): backbone logits, then the recognizer's open-set score.
+
+    method: "msp" / "max_logits" (MaxProbability) or "pdf" (U-decoder + softmax score)."""
+
+    def __init__(self, in_channels=6, num_classes=13, method="msp", blocks=(1, 2, 3, 5, 2)):
+        super().__init__()
+        self.backbone = PointTransformerSeg(Bottleneck, list(blocks), in_channels=in_channels, num_classes=num_classes)
+        self.method = method
+        self.recognizer = PTRecognizer() if method == "pdf" else None
+
+    def forward(self, data_dict, offset_host=None):
+        from .scoring import fused_scores
+        logits = self.backbone(data_dict, offset_host).float().contiguous()
+        if self.method == "pdf":
+            conf = self.recognizer(self.backbone.taps).float().contiguous()
+            score = fused_scores(logits, conf, want=("pdf_score",))["pdf_score"]
+        else:
+            key = "msp_score" if self.method == "msp" else "ml_score"
+            score = fused_scores(logits, want=(key,))[key]
+        return dict(seg_logits=logits, score=score)
+
+    @torch.no_grad()
+    def infer(self, coord: torch.Tensor, feat: torch.Tensor, offset: torch.Tensor, device=None):
+        """Host tensors in (pinned memory recommended), host score out: the end-to-end call."""
+        dev = device if device is not None else next(self.parameters()).device
+        offset_host = offset.tolist()
+        d = dict(coord=coord.to(dev, non_blocking=True), feat=feat.to(dev, non_blocking=True),
+                 offset=offset.to(dev, non_blocking=True))
+        out = self.forward(d, offset_host)
+        return out["score"].cpu(), out["seg_logits"].argmax(-1).to(torch.int32).cpu()

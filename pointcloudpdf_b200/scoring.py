@@ -58,12 +58,12 @@ def fused_scores(logits: torch.Tensor, conf: Optional[torch.Tensor] = None, offs
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         out["scene"] = torch.empty((b, 8), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        rc = lib.pob_score_fused(n, K, b, _lib.ptr(logits), _lib.ptr(conf), _lib.ptr(off32), float(beta),
-                                 _lib.ptr(out.get("msp_score")), _lib.ptr(out.get("ml_score")),
-                                 _lib.ptr(out.get("pdf_score")), _lib.ptr(out.get("msp_prob")),
-                                 _lib.ptr(out.get("max_logit")), _lib.ptr(out.get("pred")), _lib.ptr(out.get("ml_norm")),
-                                 _lib.ptr(out.get("scene")), _lib.ptr(ws), ws_bytes, _lib.current_stream(dev))
-    _lib.check(rc, "pob_score_fused")
+        n_out = sum(k != "scene" for k in out)
+        _lib.run("pob_score_fused", n, K, b, _lib.ptr(logits), _lib.ptr(conf), _lib.ptr(off32), float(beta),
+                 _lib.ptr(out.get("msp_score")), _lib.ptr(out.get("ml_score")), _lib.ptr(out.get("pdf_score")),
+                 _lib.ptr(out.get("msp_prob")), _lib.ptr(out.get("max_logit")), _lib.ptr(out.get("pred")),
+                 _lib.ptr(out.get("ml_norm")), _lib.ptr(out.get("scene")), _lib.ptr(ws), ws_bytes,
+                 _lib.current_stream(dev), alg_bytes=4 * n * (K + (conf is not None) + n_out))
     return out
 
 

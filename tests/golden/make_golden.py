@@ -59,8 +59,39 @@ def scores_small(R):
     torch.save(dict(logits=logits, conf=conf, msp=msp, ml=ml), os.path.join(HERE, "scores_small.pt"))
 
 
+def ptv1_small(R):
+    """Unmodified reference PointTransformerSeg50 + MaxProbability + PTRecognizer + the PDF score
+    line, eval mode, default init under fixed seeds (weights are NOT stored: the mirror in
+    pointcloudpdf_b200/ptv1.py reproduces them from the same seeds, see tests/test_cpu_ptv1.py)."""
+    batch = S.s3dis_batch([2500, 900], seed=2024)
+    torch.manual_seed(2024)
+    model = R.ptseg.PointTransformerSeg50(in_channels=6, num_classes=13).eval()
+    torch.manual_seed(2025)
+    rec_model = R.pt_rec.PTRecognizer().eval()
+    hooks = {}
+
+    def tap(name, mod):
+        mod.register_forward_hook(lambda m, i, o: hooks.__setitem__(name, {"forward_output": o}))
+
+    for i in range(1, 6):
+        tap(f"backbone.enc{i}", getattr(model, f"enc{i}"))
+        tap(f"backbone.dec{i}.1", getattr(model, f"dec{i}")[1])
+    with torch.no_grad():
+        logits = model(dict(coord=batch["coord"], feat=batch["feat"], offset=batch["offset"]))
+        hooks["backbone"] = {"forward_output": logits}
+        rec = R.msp.MaxProbability(method="msp")
+        rec.model_hooks = hooks
+        msp = rec({})["score"]
+        conf = rec_model(hooks)
+        pdf = torch.cat([logits, conf], -1).softmax(-1)[:, -1]  # pointpdf_v1m1_base.py:110-113
+    torch.save(dict(coord=batch["coord"], feat=batch["feat"], offset=batch["offset"], logits=logits, msp=msp,
+                    conf=conf, pdf=pdf, seeds=(2024, 2025)), os.path.join(HERE, "ptv1_small.pt"))
+    return model, rec_model
+
+
 if __name__ == "__main__":
     with ref_glue.reference_modules() as R:
         ops_small(R)
         scores_small(R)
+        ptv1_small(R)
     print("golden fixtures written to", HERE)
