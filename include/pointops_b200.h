@@ -78,10 +78,14 @@ int pob_knn_query_bruteforce(int64_t m, int nsample, int b, const float* xyz, co
  * first sample of a scene is its first row; ties go to the lowest index.  tmp (n f32) needs no
  * initialisation and is only used when a scene exceeds the register-resident capacity
  * (131072 points); it may be NULL below that.  cluster_hint: 0 = auto, or 1/2/4/8/16 CTAs per
- * scene.  A scene requesting 0 samples writes nothing (reference quirk C5 not reproduced).      */
+ * scene.  A scene requesting 0 samples writes nothing (reference quirk C5 not reproduced).
+ * grid_workspace (optional, else NULL): the workspace pob_knn_grid_build filled for the same
+ * xyz / offset, with its n (rows of xyz) and cell_pts; the kernel then walks the points in cell
+ * order and skips, exactly, every warp whose bounding box is out of the new sample's reach.
+ * The result is bit-identical with or without it.                                              */
 int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, const int* offset,
                                 const int* new_offset, float* tmp, int* idx, int cluster_hint,
-                                cudaStream_t stream);
+                                const void* grid_workspace, int64_t n, float cell_pts, cudaStream_t stream);
 
 /* --------------------------------------------------------- grouping (pointops.grouping2) --
  * grouping_{forward,backward}_cuda_launcher (src/grouping/grouping_cuda_kernel.h:14-15).

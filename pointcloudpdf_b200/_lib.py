@@ -29,7 +29,7 @@ SIGNATURES = {
     "pob_knn_grid_query": (I, [L, I, L, I, P, P, P, F, P, P, P, P, I, P]),
     "pob_knn_query": (I, [L, I, L, I, P, P, P, P, P, P, I, P, Z, P]),
     "pob_knn_query_bruteforce": (I, [L, I, I, P, P, P, P, P, P, I, P, Z, P]),
-    "pob_farthest_point_sampling": (I, [I, L, P, P, P, P, P, I, P]),
+    "pob_farthest_point_sampling": (I, [I, L, P, P, P, P, P, I, P, L, F, P]),
     "pob_grouping_forward": (I, [L, I, I, P, P, P, P]),
     "pob_grouping_backward": (I, [L, I, I, P, P, P, P]),
     "pob_subtraction_forward": (I, [L, I, I, P, P, P, P, P]),

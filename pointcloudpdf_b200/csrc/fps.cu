@@ -3,33 +3,41 @@
 // Replaces farthest_point_sampling_cuda_kernel<bs> (libs/pointops/src/sampling/
 // sampling_cuda_kernel.cu:15-129): ONE block per scene that re-reads xyz and tmp from global
 // memory every iteration and reduces through ten __syncthreads.  FPS is m-1 strictly
-// dependent iterations, so the only lever is the latency of one iteration:
-//   * one CLUSTER of up to 16 CTAs per scene (16 SMs instead of 1); the scene's coordinates
-//     and running min-distances stay in REGISTERS for the whole kernel (P points per thread),
-//     so an iteration touches no global memory at all;
-//   * argmax = two REDUX instructions per level (distances are >= 0, so their bit patterns
-//     order like unsigned ints; ties resolved to the lowest index by a second REDUX.min),
-//     one __syncthreads per CTA, and one DSMEM all-to-all + cluster barrier per iteration
-//     carrying {value, index, x, y, z} of each CTA's winner so nobody reloads coordinates.
-// Scenes too large for registers (n > C*1024*8) run the same algorithm with the points
-// streamed from global/L2 (fps_stream_kernel), using the caller's tmp buffer.
+// dependent iterations, so the only lever is the latency of one iteration.  Measured on B200
+// (profiles/r01_sync_microbench.txt): __syncthreads 15 ns (256 thr), a CTA-wide argmax by REDUX
+// ~60-75 ns, any cluster-wide exchange (cluster.sync or st.async+mbarrier) ~190-260 ns.  Design:
+//   * one CLUSTER of up to 16 CTAs per scene; the scene's coordinates and running min-distances
+//     stay in REGISTERS for the whole kernel (P points per thread, 2 warps per scheduler), so an
+//     iteration touches no global memory at all;
+//   * EXACT pruning: when the caller passes the kNN search grid of the same cloud, points are
+//     taken in cell order, so each warp owns a spatially compact run of 32*P points with a
+//     bounding box; a warp whose box is farther from the new sample than its current maximum
+//     (conservatively rounded) cannot change and skips the update -- after a few hundred
+//     samples almost every warp skips, and the iteration is pure synchronisation latency;
+//   * argmax = two REDUX instructions per level (distances are >= 0, so their bit patterns order
+//     like unsigned ints; ties resolved to the lowest ORIGINAL index by a REDUX.min), one
+//     __syncthreads per CTA, and one DSMEM all-to-all + cluster barrier per iteration carrying
+//     {value, index, x, y, z} of each CTA's winner so nobody reloads coordinates.
+// Scenes too large for registers (n > 131072) run the same algorithm with the points streamed
+// from global/L2 (fps_stream_kernel), using the caller's tmp buffer.
 //
 // Semantics: idx[s_m] = s_n; tmp = 1e10; tmp[i] = min(tmp[i], d2(i, last));
 // next = argmax tmp, LOWEST index among maxima (north_star tie rule; the reference's winner
 // depends on its block size, sampling_cuda_kernel.cu:5-10,49-59).  d2 = pob::d2_ref.
 #include "common.cuh"
+#include "grid.cuh"
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
 
 namespace pob {
 
-constexpr int FPS_THREADS = 1024;
 constexpr int FPS_MAX_CLUSTER = 16;
+constexpr int FPS_STREAM_THREADS = 1024;
 
 struct __align__(16) FpsMsg {  // one CTA's winner, 32 bytes
     unsigned bits;             // float bits of the winning tmp value
-    int idx;                   // global point index
+    int idx;                   // global (original) point index
     float x, y, z;
     int pad0, pad1, pad2;
 };
@@ -39,107 +47,209 @@ __device__ __forceinline__ void warp_argmax(unsigned bits, int gi, unsigned& wbi
     wi = __reduce_min_sync(FULL, bits == wbits ? gi : INT_MAX);
 }
 
-// One cluster (C CTAs) per scene; P points per thread held in registers.
-template <int P>
-__global__ void __launch_bounds__(FPS_THREADS, 1)
+// ---- DSMEM all-to-all without fences: st.async carries its own completion (mbarrier tx) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, int cta) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void st_async_v4(unsigned remote_addr, unsigned a, unsigned b, unsigned c, unsigned d,
+                                            unsigned remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
+                 ::"r"(remote_addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_bar) : "memory");
+}
+
+// One cluster (C CTAs of T threads) per scene; P points per thread held in registers.
+// Dynamic shared memory: float[3][T*P] copy of this CTA's coordinates (winner lookup).
+// (A variant where every warp publishes straight to every CTA -- no CTA-level stage -- was
+// measured slower: 988 vs 727 ns/iteration at 80k points; 16x more st.async per iteration.)
+template <int P, int T>
+__global__ void __launch_bounds__(T, 1)
 fps_cluster_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
-                   int* __restrict__ idx) {
+                   const SceneGrid* __restrict__ scenes, const int* __restrict__ cell_start,
+                   const float4* __restrict__ sorted, int* __restrict__ idx) {
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
-    const int rank = (int)cluster.block_rank();
+    int rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));  // volatile: never re-read inside the loop
     const int scene = blockIdx.x / C;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = T / 32;
 
     const int s_n = scene == 0 ? 0 : offset[scene - 1], e_n = offset[scene];
     const int s_m = scene == 0 ? 0 : new_offset[scene - 1], e_m = new_offset[scene];
 
-    __shared__ unsigned s_bits[32];
-    __shared__ int s_idx[32];
-    __shared__ FpsMsg s_msg[2][FPS_MAX_CLUSTER];
+    extern __shared__ float s_xyz[];  // [3][T*P]
+    __shared__ unsigned s_bits[2][NW];  // per-warp entries, double-buffered by iteration parity
+    __shared__ int s_idx[2][NW];
+    __shared__ int s_slot[2][NW];
+    __shared__ __align__(16) FpsMsg s_msg[2][FPS_MAX_CLUSTER];
+    __shared__ __align__(8) unsigned long long s_bar[2];
 
     // every CTA of the cluster takes the same branch: no barrier is skipped by part of it
     if (e_m <= s_m || e_n <= s_n) return;
+    const int n = e_n - s_n;
 
-    const int stride = C * FPS_THREADS;
-    const int first = s_n + rank * FPS_THREADS + tid;
+    // ---- load: cell order (compact warps, prunable) when a grid is given, else strided ----
+    const bool in_cells = scenes != nullptr && scenes[scene].use_grid;
     float px[P], py[P], pz[P], pt[P];
+    int pi[P];
+    float blo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, bhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    bool box_ok = true;
+    const int sbase = in_cells ? __ldg(cell_start + scenes[scene].cell_base) : 0;
 #pragma unroll
     for (int p = 0; p < P; p++) {
-        const int i = first + p * stride;
-        if (i < e_n) {
-            px[p] = __ldg(xyz + (int64_t)i * 3);
-            py[p] = __ldg(xyz + (int64_t)i * 3 + 1);
-            pz[p] = __ldg(xyz + (int64_t)i * 3 + 2);
+        // position of this register slot in the scene's point sequence
+        const int pos = in_cells ? ((rank * NW + warp) * P + p) * 32 + lane : p * (C * T) + rank * T + tid;
+        if (pos < n) {
+            if (in_cells) {
+                const float4 v = __ldg(sorted + sbase + pos);
+                px[p] = v.x; py[p] = v.y; pz[p] = v.z; pi[p] = __float_as_int(v.w);
+            } else {
+                const int i = s_n + pos;
+                px[p] = __ldg(xyz + (int64_t)i * 3); py[p] = __ldg(xyz + (int64_t)i * 3 + 1); pz[p] = __ldg(xyz + (int64_t)i * 3 + 2);
+                pi[p] = i;
+            }
             pt[p] = PLACEHOLDER_D2;
+            box_ok = box_ok && isfinite(px[p]) && isfinite(py[p]) && isfinite(pz[p]);
+            blo[0] = fminf(blo[0], px[p]); bhi[0] = fmaxf(bhi[0], px[p]);
+            blo[1] = fminf(blo[1], py[p]); bhi[1] = fmaxf(bhi[1], py[p]);
+            blo[2] = fminf(blo[2], pz[p]); bhi[2] = fmaxf(bhi[2], pz[p]);
         } else {
             px[p] = py[p] = pz[p] = 0.f;
             pt[p] = -1.f;  // never a maximum: fminf keeps it at -1
+            pi[p] = INT_MAX;
+        }
+        const int slot = (warp * P + p) * 32 + lane;
+        s_xyz[slot] = px[p]; s_xyz[T * P + slot] = py[p]; s_xyz[2 * T * P + slot] = pz[p];
+    }
+    // warp bounding box (only meaningful, and only used, in cell order)
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            blo[a] = fminf(blo[a], __shfl_xor_sync(FULL, blo[a], o));
+            bhi[a] = fmaxf(bhi[a], __shfl_xor_sync(FULL, bhi[a], o));
         }
     }
+    const bool prune = in_cells && __all_sync(FULL, box_ok);
+
     float ox = __ldg(xyz + (int64_t)s_n * 3), oy = __ldg(xyz + (int64_t)s_n * 3 + 1), oz = __ldg(xyz + (int64_t)s_n * 3 + 2);
-    if (rank == 0 && tid == 0) idx[s_m] = s_n;
+    const bool writer = rank == 0 && tid == 0;
+    if (writer) idx[s_m] = s_n;
+    int* out = idx + s_m;
 
-    for (int j = s_m + 1; j < e_m; j++) {
-        // ---- update the running minimum, thread-local argmax (strict '>' keeps the lowest index) ----
-        float best = 0.f;
-        int bp = -1;
-#pragma unroll
-        for (int p = 0; p < P; p++) {
-            const float d = d2_ref(px[p], py[p], pz[p], ox, oy, oz);
-            const float t = fminf(d, pt[p]);
-            pt[p] = t;
-            if (t > best || (bp < 0 && t >= 0.f)) { best = t; bp = p; }
+    // exchange plumbing: one mbarrier per parity, armed for C messages of 32 bytes
+    const unsigned bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]);
+    unsigned rslot0 = 0, rslot1 = 0, rbar0 = 0, rbar1 = 0;
+    if (C > 1) {
+        if (tid == 0) {
+            mbar_init(bar0, 1);
+            mbar_init(bar1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(bar0, C * (int)sizeof(FpsMsg));
+            mbar_expect_tx(bar1, C * (int)sizeof(FpsMsg));
         }
-        // a thread with no valid point offers (0, INT_MAX): it loses every tie against a real point
-        const int gi = bp >= 0 ? first + bp * stride : INT_MAX;
-        float bx = 0.f, by = 0.f, bz = 0.f;
-#pragma unroll
-        for (int p = 0; p < P; p++) if (p == bp) { bx = px[p]; by = py[p]; bz = pz[p]; }
-
-        // ---- CTA argmax: REDUX per warp, one barrier, REDUX over the 32 warp winners ----
-        unsigned wbits; int wi;
-        warp_argmax(__float_as_uint(best), gi, wbits, wi);
-        if (lane == 0) { s_bits[warp] = wbits; s_idx[warp] = wi; }
+        if (warp == 0 && lane < C) {  // lane l talks to CTA l
+            rslot0 = mapa_u32(smem_u32(&s_msg[0][rank]), lane);
+            rslot1 = mapa_u32(smem_u32(&s_msg[1][rank]), lane);
+            rbar0 = mapa_u32(bar0, lane);
+            rbar1 = mapa_u32(bar1, lane);
+        }
+        cluster.sync();  // every CTA's barriers exist before anyone writes remotely
+    } else {
         __syncthreads();
-        unsigned cbits; int ci;
-        warp_argmax(s_bits[lane], s_idx[lane], cbits, ci);
-
-        // ---- the warp that owns the CTA winner publishes it (with coordinates) to every CTA ----
-        const int par = j & 1;
-        const unsigned own = __ballot_sync(FULL, gi == ci && ci != INT_MAX);
-        if (own) {
-            const int ol = __ffs(own) - 1;
-            FpsMsg msg;
-            msg.bits = cbits; msg.idx = ci;
-            msg.x = __shfl_sync(FULL, bx, ol); msg.y = __shfl_sync(FULL, by, ol); msg.z = __shfl_sync(FULL, bz, ol);
-            msg.pad0 = msg.pad1 = msg.pad2 = 0;
-            if (lane < C) {
-                FpsMsg* dst = cluster.map_shared_rank(&s_msg[par][rank], lane);
-                *dst = msg;
-            }
-        } else if (ci == INT_MAX && warp == 0 && lane < C) {
-            // CTA without any valid point (rank beyond the scene): publish a losing entry
-            FpsMsg msg = {0u, INT_MAX, 0.f, 0.f, 0.f, 0, 0, 0};
-            *cluster.map_shared_rank(&s_msg[par][rank], lane) = msg;
-        }
-        cluster.sync();  // release/acquire: all C messages of this iteration are visible
-
-        // ---- every thread picks the cluster winner from its own CTA's copy ----
-        const FpsMsg mine = s_msg[par][lane < C ? lane : 0];
-        unsigned gbits; int gidx;
-        warp_argmax(lane < C ? mine.bits : 0u, lane < C ? mine.idx : INT_MAX, gbits, gidx);
-        const unsigned who = __ballot_sync(FULL, lane < C && mine.idx == gidx);
-        const int wl = __ffs(who) - 1;
-        ox = __shfl_sync(FULL, mine.x, wl); oy = __shfl_sync(FULL, mine.y, wl); oz = __shfl_sync(FULL, mine.z, wl);
-        if (rank == 0 && tid == 0) idx[j] = gidx;
-        // s_bits/s_idx are rewritten only after the next iteration's compute; the cluster barrier
-        // above already orders this iteration's reads before those writes.
     }
+
+    unsigned wbits = __float_as_uint(PLACEHOLDER_D2);  // this warp's current maximum (cached while it skips)
+    int wi = INT_MAX, wslot = 0;
+    bool first_pass = true;  // every warp computes its entry once before it may start skipping
+    const int iters = e_m - s_m - 1;
+
+    for (int it = 0; it < iters; it++) {
+        const int par = it & 1;
+        // ---- can the new sample lower anything this warp owns? (exact, conservative) ----
+        bool touch = true;
+        if (prune && !first_pass) {
+            const float ex = fmaxf(fmaxf(blo[0] - ox, ox - bhi[0]), 0.f);
+            const float ey = fmaxf(fmaxf(blo[1] - oy, oy - bhi[1]), 0.f);
+            const float ez = fmaxf(fmaxf(blo[2] - oz, oz - bhi[2]), 0.f);
+            const float b2 = __fmaf_rn(ez, ez, __fmaf_rn(ex, ex, __fmul_rn(ey, ey)));
+            // every d2_ref(point, sample) >= b2 * (1 - 1e-6); if even b2 * 0.99999 >= max tmp nothing changes
+            touch = !(b2 * 0.99999f >= __uint_as_float(wbits));
+        }
+        first_pass = false;
+        if (touch) {
+            float m = 0.f;
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                const float d = d2_ref(px[p], py[p], pz[p], ox, oy, oz);
+                pt[p] = fminf(d, pt[p]);
+                m = fmaxf(m, pt[p]);
+            }
+            wbits = __reduce_max_sync(FULL, __float_as_uint(m));
+            // lowest original index among this warp's maxima, and where it sits
+            int cand = INT_MAX, cp = 0;
+#pragma unroll
+            for (int p = 0; p < P; p++)
+                if (__float_as_uint(pt[p]) == wbits && pi[p] < cand) { cand = pi[p]; cp = p; }
+            wi = __reduce_min_sync(FULL, cand);
+            const unsigned own = __ballot_sync(FULL, cand == wi && wi != INT_MAX);
+            const int ol = own ? __ffs(own) - 1 : 0;
+            wslot = __shfl_sync(FULL, (warp * P + cp) * 32 + lane, ol);
+        }
+        if (lane == 0) { s_bits[par][warp] = wbits; s_idx[par][warp] = wi; s_slot[par][warp] = wslot; }
+        __syncthreads();
+
+        // ---- CTA argmax over the NW warp entries (every warp computes it redundantly) ----
+        const unsigned eb = lane < NW ? s_bits[par][lane] : 0u;
+        const int ei = lane < NW ? s_idx[par][lane] : INT_MAX;
+        unsigned cbits; int ci;
+        warp_argmax(eb, ei, cbits, ci);
+        const unsigned whow = __ballot_sync(FULL, lane < NW && ei == ci);
+        const int cslot = s_slot[par][whow ? __ffs(whow) - 1 : 0];
+        float cx = s_xyz[cslot], cy = s_xyz[T * P + cslot], cz = s_xyz[2 * T * P + cslot];
+        int gidx = ci;
+        if (C > 1) {
+            // ---- all-to-all of the CTA winners: 32-byte st.async per peer, completion on the
+            //      receiver's mbarrier (no cluster-scope fence, nothing waits on global stores) ----
+            if (warp == 0 && lane < C) {
+                const unsigned rs = par ? rslot1 : rslot0, rb = par ? rbar1 : rbar0;
+                st_async_v4(rs, cbits, (unsigned)ci, __float_as_uint(cx), __float_as_uint(cy), rb);
+                st_async_v4(rs + 16, __float_as_uint(cz), 0u, 0u, 0u, rb);
+            }
+            mbar_wait(par ? bar1 : bar0, (unsigned)(it >> 1) & 1u);
+            if (tid == 0) mbar_expect_tx(par ? bar1 : bar0, C * (int)sizeof(FpsMsg));  // re-arm for it + 2
+            const FpsMsg mine = s_msg[par][lane < C ? lane : 0];
+            unsigned gbits;
+            warp_argmax(lane < C ? mine.bits : 0u, lane < C ? mine.idx : INT_MAX, gbits, gidx);
+            const unsigned who = __ballot_sync(FULL, lane < C && mine.idx == gidx);
+            const int wl = who ? __ffs(who) - 1 : 0;
+            cx = __shfl_sync(FULL, mine.x, wl); cy = __shfl_sync(FULL, mine.y, wl); cz = __shfl_sync(FULL, mine.z, wl);
+        }
+        ox = cx; oy = cy; oz = cz;
+        if (writer) out[it + 1] = gidx;
+    }
+    if (C > 1) cluster.sync();  // nobody leaves while a peer may still be writing into its shared memory
 }
 
 // Same algorithm with the points left in global memory (L2-resident for any realistic scene):
 // the fallback for scenes that do not fit the register-resident kernel.
-__global__ void __launch_bounds__(FPS_THREADS, 1)
+__global__ void __launch_bounds__(FPS_STREAM_THREADS, 1)
 fps_stream_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
                   float* __restrict__ tmp, int* __restrict__ idx) {
     cg::cluster_group cluster = cg::this_cluster();
@@ -154,8 +264,8 @@ fps_stream_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
     __shared__ FpsMsg s_msg[2][FPS_MAX_CLUSTER];
     if (e_m <= s_m || e_n <= s_n) return;
 
-    const int stride = C * FPS_THREADS;
-    const int first = s_n + rank * FPS_THREADS + tid;
+    const int stride = C * FPS_STREAM_THREADS;
+    const int first = s_n + rank * FPS_STREAM_THREADS + tid;
     for (int i = first; i < e_n; i += stride) tmp[i] = PLACEHOLDER_D2;
     float ox = __ldg(xyz + (int64_t)s_n * 3), oy = __ldg(xyz + (int64_t)s_n * 3 + 1), oz = __ldg(xyz + (int64_t)s_n * 3 + 2);
     if (rank == 0 && tid == 0) idx[s_m] = s_n;
@@ -189,19 +299,17 @@ fps_stream_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
         unsigned gbits; int gidx;
         warp_argmax(lane < C ? mine.bits : 0u, lane < C ? mine.idx : INT_MAX, gbits, gidx);
         const unsigned who = __ballot_sync(FULL, lane < C && mine.idx == gidx);
-        const int wl = __ffs(who) - 1;
+        const int wl = who ? __ffs(who) - 1 : 0;
         ox = __shfl_sync(FULL, mine.x, wl); oy = __shfl_sync(FULL, mine.y, wl); oz = __shfl_sync(FULL, mine.z, wl);
         if (rank == 0 && tid == 0) idx[j] = gidx;
     }
 }
 
-template <typename K>
-static int launch_cluster(K kernel, int b, int C, cudaStream_t stream, const float* xyz, const int* offset,
-                          const int* new_offset, float* tmp, int* idx, bool pass_tmp) {
+static int launch_cluster(const void* kernel, int b, int C, int threads, size_t smem, cudaStream_t stream, void** args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(b * C));
-    cfg.blockDim = dim3(FPS_THREADS);
-    cfg.dynamicSmemBytes = 0;
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -210,12 +318,21 @@ static int launch_cluster(K kernel, int b, int C, cudaStream_t stream, const flo
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (C > 8) POB_CHECK(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    void* args_tmp[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&tmp, (void*)&idx};
-    void* args[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&idx};
-    POB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)kernel, pass_tmp ? args_tmp : args));
+    if (C > 8) POB_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    if (smem > 48 * 1024) POB_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    POB_CHECK(cudaLaunchKernelExC(&cfg, kernel, args));
     pob_count_launches(1);
     return 0;
+}
+
+template <int T>
+static int launch_resident(int P, int b, int C, cudaStream_t stream, void** args) {
+#define POB_FPS_CASE(PP) \
+    if (P <= PP) return launch_cluster((const void*)fps_cluster_kernel<PP, T>, b, C, T, sizeof(float) * 3 * T * PP, stream, args)
+    POB_FPS_CASE(1); POB_FPS_CASE(2); POB_FPS_CASE(4); POB_FPS_CASE(6); POB_FPS_CASE(8); POB_FPS_CASE(12);
+    POB_FPS_CASE(16); POB_FPS_CASE(20); POB_FPS_CASE(24); POB_FPS_CASE(32);
+#undef POB_FPS_CASE
+    return POB_ERR_UNSUPPORTED;
 }
 
 }  // namespace pob
@@ -223,32 +340,44 @@ static int launch_cluster(K kernel, int b, int C, cudaStream_t stream, const flo
 using namespace pob;
 
 // farthest_point_sampling_cuda_launcher(b, n, xyz, offset, new_offset, tmp, idx)
-// (sampling_cuda_kernel.h:13) + stream.  n_max = largest scene (the reference's `n`); tmp (n
-// floats) is only touched when a scene exceeds the register-resident capacity, and needs no
-// initialisation.  cluster_hint: 0 = choose, else force 1/2/4/8/16 CTAs per scene.
+// (sampling_cuda_kernel.h:13) + the optional kNN grid of the same (xyz, offset) + stream.
+// n_max = largest scene (the reference's `n`); tmp (n floats) is only touched when a scene
+// exceeds the register-resident capacity (131072 points) and needs no initialisation.
+// grid_workspace: NULL, or the workspace pob_knn_grid_build filled for the same xyz/offset with
+// the same n, b, cell_pts -- enables exact spatial pruning; results are identical either way.
+// cluster_hint: 0 = choose, else force 1/2/4/8/16 CTAs per scene.
 POB_API int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, const int* offset,
                                         const int* new_offset, float* tmp, int* idx, int cluster_hint,
-                                        cudaStream_t stream) {
+                                        const void* grid_workspace, int64_t n, float cell_pts, cudaStream_t stream) {
     if (b < 1 || n_max < 0 || !offset || !new_offset || !idx) return POB_ERR_BAD_ARG;
     if (n_max == 0) return 0;
     if (!xyz) return POB_ERR_BAD_ARG;
+    const SceneGrid* scenes = nullptr;
+    const int* cell_start = nullptr;
+    const float4* sorted = nullptr;
+    if (grid_workspace) {
+        if (!(cell_pts >= 0.25f)) cell_pts = 0.25f;
+        const GridLayout L = grid_layout(n, b, cell_pts);
+        const char* ws = (const char*)grid_workspace;
+        scenes = (const SceneGrid*)(ws + L.off_scene);
+        cell_start = (const int*)(ws + L.off_start);
+        sorted = (const float4*)(ws + L.off_sorted);
+    }
+    constexpr int T = 256;      // 2 warps per scheduler: the per-iteration overhead scales with warps
+    constexpr int PMAX = 32;    // registers: 5 per point + ~40
     int C = cluster_hint;
     if (C != 1 && C != 2 && C != 4 && C != 8 && C != 16) {
-        // per-iteration cost ~ 8 warps/SMSP * 9 instr * P  vs  ~400 cycles of cluster exchange
-        C = n_max <= 6 * 1024 ? 1 : (n_max <= 24 * 1024 ? 8 : 16);
+        // ~200 ns of cluster exchange per iteration buys a 1/C share of the update work
+        C = n_max <= 4096 ? 1 : (n_max <= 16384 ? 4 : (n_max <= 40960 ? 8 : 16));
     }
-    const int64_t per_thread = ceil_div(n_max, (int64_t)C * FPS_THREADS);
-    if (per_thread > 8) {
-        C = 16;
-        if (ceil_div(n_max, (int64_t)C * FPS_THREADS) > 8) {
-            if (!tmp) return POB_ERR_BAD_ARG;
-            return launch_cluster(fps_stream_kernel, b, C, stream, xyz, offset, new_offset, tmp, idx, true);
-        }
+    while (C < 16 && ceil_div(n_max, (int64_t)C * T) > PMAX) C *= 2;
+    const int64_t P = ceil_div(n_max, (int64_t)C * T);
+    if (P > PMAX) {
+        if (!tmp) return POB_ERR_BAD_ARG;
+        void* args[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&tmp, (void*)&idx};
+        return launch_cluster((const void*)fps_stream_kernel, b, 16, FPS_STREAM_THREADS, 0, stream, args);
     }
-    const int64_t P = ceil_div(n_max, (int64_t)C * FPS_THREADS);
-    if (P <= 1) return launch_cluster(fps_cluster_kernel<1>, b, C, stream, xyz, offset, new_offset, tmp, idx, false);
-    if (P <= 2) return launch_cluster(fps_cluster_kernel<2>, b, C, stream, xyz, offset, new_offset, tmp, idx, false);
-    if (P <= 4) return launch_cluster(fps_cluster_kernel<4>, b, C, stream, xyz, offset, new_offset, tmp, idx, false);
-    if (P <= 6) return launch_cluster(fps_cluster_kernel<6>, b, C, stream, xyz, offset, new_offset, tmp, idx, false);
-    return launch_cluster(fps_cluster_kernel<8>, b, C, stream, xyz, offset, new_offset, tmp, idx, false);
+    void* args[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&scenes, (void*)&cell_start,
+                    (void*)&sorted, (void*)&idx};
+    return launch_resident<T>((int)P, b, C, stream, args);
 }

@@ -4,8 +4,12 @@ from __future__ import annotations
 import torch
 from torch.autograd import Function
 
+import os
+
 from .. import _lib
 from . import _common as C
+
+USE_GRID = os.environ.get("POINTOPS_B200_FPS_GRID", "1") != "0"
 
 
 class FarthestPointSampling(Function):
@@ -35,8 +39,12 @@ class FarthestPointSampling(Function):
         with torch.cuda.device(xyz.device):
             noff = C.host_offset(new_offset)
             flops = sum(10 * max(mb - 1, 0) * nb for nb, mb in zip(sizes, C.scene_sizes(noff)))
+            # the search grid of this cloud (built once, reused by the kNN queries that follow in
+            # TransitionDown) gives the kernel cell-ordered points for exact pruning
+            grid = C.get_grid(xyz, offset) if (USE_GRID and n_max > 2048) else None
             _lib.run("pob_farthest_point_sampling", b, n_max, _lib.ptr(xyz), _lib.ptr(offset), _lib.ptr(new_offset),
-                     _lib.ptr(tmp), _lib.ptr(idx), 0, _lib.current_stream(xyz.device),
+                     _lib.ptr(tmp), _lib.ptr(idx), 0, _lib.ptr(grid.workspace if grid else None),
+                     xyz.shape[0], grid.cell_pts if grid else 0.0, _lib.current_stream(xyz.device),
                      alg_bytes=12 * xyz.shape[0] + 4 * m, alg_flops=flops)
         ctx.mark_non_differentiable(idx)
         return idx

@@ -14,7 +14,7 @@ REL = 1e-5  # stated tolerance for f32 accumulation-order differences
 
 
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
-    a, b = a.double().cpu(), b.double().cpu()
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
@@ -138,10 +138,14 @@ def test_fps_every_cluster_size_same_result(cuda, oracle, cluster):
     ref = oracle.farthest_point_sampling(xyz, offset, new_offset)
     xyz_d, off_d, noff_d = xyz.to(cuda), offset.to(cuda), new_offset.to(cuda)
     out = torch.empty(2000, dtype=torch.int32, device=cuda)
-    rc = _lib.load().pob_farthest_point_sampling(2, 6000, _lib.ptr(xyz_d), _lib.ptr(off_d), _lib.ptr(noff_d), None,
-                                                 _lib.ptr(out), cluster, _lib.current_stream(cuda))
-    assert rc == 0
-    assert torch.equal(out.cpu(), ref)
+    from pointcloudpdf_b200.pointops import _common as C
+    grid = C.NeighbourGrid(xyz_d, off_d)
+    for ws, n, cp in ((None, 0, 0.0), (_lib.ptr(grid.workspace), 8000, grid.cell_pts)):  # strided / cell order + pruning
+        out.zero_()
+        rc = _lib.load().pob_farthest_point_sampling(2, 6000, _lib.ptr(xyz_d), _lib.ptr(off_d), _lib.ptr(noff_d), None,
+                                                     _lib.ptr(out), cluster, ws, n, cp, _lib.current_stream(cuda))
+        assert rc == 0
+        assert torch.equal(out.cpu(), ref)
 
 
 def test_fps_ties_lowest_index(cuda, oracle):
