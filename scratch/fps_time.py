@@ -21,9 +21,9 @@ def run(n, m, cluster, use_grid, reps=3):
     return best, out
 for n, m in ((80000, 20000), (20000, 5000), (5000, 1250), (1250, 312)):
     ref = None
-    for use_grid in (0, 1):
-        for cl in (1, 2, 4, 8, 16):
-            if n / (cl * 256) > 32: continue
+    for use_grid in (1,):
+        for cl in (1, 4, 8, 16, 101, 104, 108, 116):
+            if n / ((cl % 100) * (512 if cl >= 100 else 256)) > (16 if cl >= 100 else 32): continue
             ms, out = run(n, m, cl, use_grid)
             if ref is None: ref = out.clone()
             same = torch.equal(out, ref)
