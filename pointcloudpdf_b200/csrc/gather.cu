@@ -16,6 +16,7 @@
 // width (32..512) qualifies; other shapes take the scalar kernels at the bottom, which are
 // still CUDA: there is no CPU fallback anywhere.
 #include "common.cuh"
+#include "gather_fast.cuh"
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 
@@ -456,6 +457,137 @@ static inline unsigned warp_grid(int64_t warps_needed) {
     return grid_for(warps_needed * 32, GATHER_THREADS, 8, 4);
 }
 
+
+// ------------------------------------------------------------ fast-path dispatch ----------
+// lanes per row of the compile-time-tiled kernels: C = 4 * LPR, LPR a power of two <= 32
+static inline int lpr_of(int c) {
+    if (c <= 0 || c % 4) return 0;
+    const int v = c / 4;
+    return (v <= 32 && (v & (v - 1)) == 0) ? v : 0;
+}
+static inline int shift_of(int v) {  // log2 for powers of two, else -1
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int s = 0;
+    while ((1 << s) < v) s++;
+    return s;
+}
+static inline unsigned fast_grid(int64_t warps_needed) {
+    const int64_t ctas = ceil_div(warps_needed, FAST_THREADS / 32);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    return (unsigned)(ctas < 1 ? 1 : (ctas < cap ? ctas : cap));
+}
+#define POB_LPR_SWITCH(lpr, M) \
+    switch (lpr) { case 1: M(1); break; case 2: M(2); break; case 4: M(4); break; case 8: M(8); break; \
+                   case 16: M(16); break; case 32: M(32); break; default: break; }
+
+template <typename T, bool SUB, bool MASKED>
+static bool launch_gather_fast(int lpr, int64_t rows, int ns, const T* in, const float* in1, const int* idx, float* out,
+                               cudaStream_t stream) {
+    if (!lpr) return false;
+#define M(L) { constexpr int U = (L >= 8) ? 8 : 4; constexpr int R = (32 / L) * U; \
+        gather_rows_fast<T, L, U, SUB, MASKED><<<fast_grid(ceil_div(rows, R)), FAST_THREADS, 0, stream>>>( \
+            rows, ns, shift_of(ns), in, (const float4*)in1, idx, (float4*)out); }
+    POB_LPR_SWITCH(lpr, M)
+#undef M
+    return true;
+}
+
+static bool launch_scatter_fast(int lpr, int64_t rows, float sign, const float* gout, const int* idx, float* gin,
+                                cudaStream_t stream) {
+    if (!lpr) return false;
+#define M(L) { constexpr int U = (L >= 8) ? 8 : 4; constexpr int R = (32 / L) * U; \
+        scatter_rows_fast<L, U><<<fast_grid(ceil_div(rows, R)), FAST_THREADS, 0, stream>>>( \
+            rows, sign, (const float4*)gout, idx, (float4*)gin); }
+    POB_LPR_SWITCH(lpr, M)
+#undef M
+    return true;
+}
+
+// whole-point tiles exist when nsample is 8 or 16 and a multiple of the rows a warp holds side by side
+static inline bool ns_tiled(int lpr, int ns) { return lpr && (ns == 8 || ns == 16) && ns % (32 / lpr) == 0; }
+
+template <int L, int NS> static constexpr bool tile_ok() { return NS % (32 / L) == 0; }
+
+static bool launch_reduce_fast(int lpr, int ns, int64_t n, const float* gout, float* g1, cudaStream_t stream) {
+    if (!ns_tiled(lpr, ns)) return false;
+#define M(L) { if (ns == 8) { if constexpr (tile_ok<L, 8>()) { constexpr int U = ((8 / (32 / L)) > 8) ? 8 / (32 / L) : 8; \
+            reduce_neighbours_fast<L, 8><<<fast_grid(ceil_div(n, (U * (32 / L)) / 8)), FAST_THREADS, 0, stream>>>(n, (const float4*)gout, (float4*)g1); } } \
+        else { if constexpr (tile_ok<L, 16>()) { constexpr int U = ((16 / (32 / L)) > 8) ? 16 / (32 / L) : 8; \
+            reduce_neighbours_fast<L, 16><<<fast_grid(ceil_div(n, (U * (32 / L)) / 16)), FAST_THREADS, 0, stream>>>(n, (const float4*)gout, (float4*)g1); } } }
+    POB_LPR_SWITCH(lpr, M)
+#undef M
+    return true;
+}
+
+static bool launch_agg_fwd_fast(int lpr, int ns, int64_t n, int wvec, const float* in, const float* pos, const float* w,
+                                const int* idx, float* out, cudaStream_t stream) {
+    if (!ns_tiled(lpr, ns)) return false;
+#define M(L) { if (ns == 8) { if constexpr (tile_ok<L, 8>()) { constexpr int U = ((8 / (32 / L)) > 8) ? 8 / (32 / L) : 8; \
+            aggregation_fwd_fast<L, 8><<<fast_grid(ceil_div(n, (U * (32 / L)) / 8)), FAST_THREADS, 0, stream>>>( \
+                n, wvec, (const float4*)in, (const float4*)pos, (const float4*)w, idx, (float4*)out); } } \
+        else { if constexpr (tile_ok<L, 16>()) { constexpr int U = ((16 / (32 / L)) > 8) ? 16 / (32 / L) : 8; \
+            aggregation_fwd_fast<L, 16><<<fast_grid(ceil_div(n, (U * (32 / L)) / 16)), FAST_THREADS, 0, stream>>>( \
+                n, wvec, (const float4*)in, (const float4*)pos, (const float4*)w, idx, (float4*)out); } } }
+    POB_LPR_SWITCH(lpr, M)
+#undef M
+    return true;
+}
+
+static bool launch_agg_bwd_fast(int lpr, int ns, int64_t n, int wvec, const float* in, const float* pos, const float* w,
+                                const int* idx, const float* gout, float* gin, float* gpos, float* gw,
+                                cudaStream_t stream) {
+    if (!ns_tiled(lpr, ns)) return false;
+#define M(L) { if (ns == 8) { if constexpr (tile_ok<L, 8>()) { constexpr int U = ((8 / (32 / L)) > 4) ? 8 / (32 / L) : 4; \
+            aggregation_bwd_fast<L, 8><<<fast_grid(ceil_div(n, (U * (32 / L)) / 8)), FAST_THREADS, 0, stream>>>( \
+                n, wvec, (const float4*)in, (const float4*)pos, (const float4*)w, idx, (const float4*)gout, \
+                (float4*)gin, (float4*)gpos, (float4*)gw); } } \
+        else { if constexpr (tile_ok<L, 16>()) { constexpr int U = ((16 / (32 / L)) > 4) ? 16 / (32 / L) : 4; \
+            aggregation_bwd_fast<L, 16><<<fast_grid(ceil_div(n, (U * (32 / L)) / 16)), FAST_THREADS, 0, stream>>>( \
+                n, wvec, (const float4*)in, (const float4*)pos, (const float4*)w, idx, (const float4*)gout, \
+                (float4*)gin, (float4*)gpos, (float4*)gw); } } }
+    POB_LPR_SWITCH(lpr, M)
+#undef M
+    return true;
+}
+
+static bool launch_interp_fwd_fast(int lpr, int64_t n, int k, const float* in, const int* idx, const float* w, float* out,
+                                   cudaStream_t stream) {
+    if (!lpr) return false;
+#define M(L) { constexpr int U = 4; constexpr int R = (32 / L) * U; \
+        interpolation_fwd_fast<L, U><<<fast_grid(ceil_div(n, R)), FAST_THREADS, 0, stream>>>( \
+            n, k, (const float4*)in, idx, w, (float4*)out); }
+    POB_LPR_SWITCH(lpr, M)
+#undef M
+    return true;
+}
+
+template <typename T>
+static int launch_group_xyz_fwd_fast(int lpr, int64_t m, int ns, const T* feat, const float* xyz, const float* new_xyz,
+                                     const int* idx, float* out, cudaStream_t stream) {
+    const int per = ns * (4 * lpr + 3);
+    const size_t smem = sizeof(float) * (size_t)((per + 3) & ~3) * (FAST_THREADS / 32);
+    if (smem > 200 * 1024) return -1;
+#define M(L) { auto kern = group_xyz_fwd_fast<T, L>; \
+        if (smem > 48 * 1024) POB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<fast_grid(m), FAST_THREADS, smem, stream>>>(m, ns, feat, xyz, new_xyz, idx, out); }
+    POB_LPR_SWITCH(lpr, M)
+#undef M
+    return 0;
+}
+
+static int launch_group_xyz_bwd_fast(int lpr, int64_t m, int ns, const float* gout, const int* idx, float* gfeat,
+                                     cudaStream_t stream) {
+    const int per = ns * (4 * lpr + 3);
+    const size_t smem = sizeof(float) * (size_t)((per + 3) & ~3) * (FAST_THREADS / 32);
+    if (smem > 200 * 1024) return -1;
+#define M(L) { auto kern = group_xyz_bwd_fast<L>; \
+        if (smem > 48 * 1024) POB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<fast_grid(m), FAST_THREADS, smem, stream>>>(m, ns, gout, idx, (float4*)gfeat); }
+    POB_LPR_SWITCH(lpr, M)
+#undef M
+    return 0;
+}
+
 }  // namespace pob
 
 using namespace pob;
@@ -470,7 +602,9 @@ POB_API int pob_grouping_forward(int64_t m, int nsample, int c, const float* inp
     if (rows == 0) return 0;
     if (!input || !idx || !output) return POB_ERR_BAD_ARG;
     const RowTile t = row_tile(c);
-    if (t.ok && aligned16(input) && aligned16(output)) {
+    if (aligned16(input) && aligned16(output) &&
+        launch_gather_fast<float, false, false>(lpr_of(c), rows, nsample, input, nullptr, idx, output, stream)) {
+    } else if (t.ok && aligned16(input) && aligned16(output)) {
         gather_rows_kernel<false><<<warp_grid(ceil_div(rows, t.spar * 4)), GATHER_THREADS, 0, stream>>>(
             rows, nsample, t, input, nullptr, idx, output);
     } else {
@@ -490,7 +624,9 @@ POB_API int pob_grouping_backward(int64_t m, int nsample, int c, const float* gr
     if (rows == 0) return 0;
     if (!grad_output || !idx || !grad_input) return POB_ERR_BAD_ARG;
     const RowTile t = row_tile(c);
-    if (t.ok && aligned16(grad_output) && aligned16(grad_input)) {
+    if (aligned16(grad_output) && aligned16(grad_input) &&
+        launch_scatter_fast(lpr_of(c), rows, 1.f, grad_output, idx, grad_input, stream)) {
+    } else if (t.ok && aligned16(grad_output) && aligned16(grad_input)) {
         scatter_rows_kernel<<<warp_grid(ceil_div(rows, t.spar * 4)), GATHER_THREADS, 0, stream>>>(
             rows, t, 1.f, grad_output, idx, grad_input);
     } else {
@@ -509,7 +645,9 @@ POB_API int pob_subtraction_forward(int64_t n, int nsample, int c, const float* 
     if (rows == 0) return 0;
     if (!input1 || !input2 || !idx || !output) return POB_ERR_BAD_ARG;
     const RowTile t = row_tile(c);
-    if (t.ok && aligned16(input1) && aligned16(input2) && aligned16(output)) {
+    if (aligned16(input1) && aligned16(input2) && aligned16(output) &&
+        launch_gather_fast<float, true, false>(lpr_of(c), rows, nsample, input2, input1, idx, output, stream)) {
+    } else if (t.ok && aligned16(input1) && aligned16(input2) && aligned16(output)) {
         gather_rows_kernel<true><<<warp_grid(ceil_div(rows, t.spar * 4)), GATHER_THREADS, 0, stream>>>(
             rows, nsample, t, input2, input1, idx, output);
     } else {
@@ -530,9 +668,11 @@ POB_API int pob_subtraction_backward(int64_t n, int nsample, int c, const int* i
     if (!idx || !grad_output || !grad_input1 || !grad_input2) return POB_ERR_BAD_ARG;
     const RowTile t = row_tile(c);
     if (t.ok && aligned16(grad_output) && aligned16(grad_input1) && aligned16(grad_input2)) {
-        reduce_neighbours_kernel<<<warp_grid(n), GATHER_THREADS, 0, stream>>>(n, nsample, t, grad_output, grad_input1);
-        scatter_rows_kernel<<<warp_grid(ceil_div(rows, t.spar * 4)), GATHER_THREADS, 0, stream>>>(
-            rows, t, -1.f, grad_output, idx, grad_input2);
+        if (!launch_reduce_fast(lpr_of(c), nsample, n, grad_output, grad_input1, stream))
+            reduce_neighbours_kernel<<<warp_grid(n), GATHER_THREADS, 0, stream>>>(n, nsample, t, grad_output, grad_input1);
+        if (!launch_scatter_fast(lpr_of(c), rows, -1.f, grad_output, idx, grad_input2, stream))
+            scatter_rows_kernel<<<warp_grid(ceil_div(rows, t.spar * 4)), GATHER_THREADS, 0, stream>>>(
+                rows, t, -1.f, grad_output, idx, grad_input2);
     } else {
         reduce_neighbours_scalar_kernel<<<grid_for(n * c, 256, 8), 256, 0, stream>>>(n, nsample, c, grad_output,
                                                                                      grad_input1);
@@ -563,8 +703,9 @@ POB_API int pob_aggregation_forward(int64_t n, int nsample, int c, int w_c, cons
     const RowTile t = row_tile(c);
     int wvec = 0;
     if (agg_fast(t, c, w_c, &wvec) && aligned16(input) && aligned16(position) && aligned16(weight) && aligned16(output)) {
-        aggregation_fwd_kernel<<<warp_grid(n), GATHER_THREADS, 0, stream>>>(n, nsample, t, wvec, input, position,
-                                                                            weight, idx, output);
+        if (!launch_agg_fwd_fast(lpr_of(c), nsample, n, wvec, input, position, weight, idx, output, stream))
+            aggregation_fwd_kernel<<<warp_grid(n), GATHER_THREADS, 0, stream>>>(n, nsample, t, wvec, input, position,
+                                                                                weight, idx, output);
     } else {
         aggregation_fwd_scalar_kernel<<<grid_for(n * c, 256, 8), 256, 0, stream>>>(n, nsample, c, w_c, input, position,
                                                                                    weight, idx, output);
@@ -588,8 +729,10 @@ POB_API int pob_aggregation_backward(int64_t n, int nsample, int c, int w_c, con
     int wvec = 0;
     if (agg_fast(t, c, w_c, &wvec) && aligned16(input) && aligned16(position) && aligned16(weight) &&
         aligned16(grad_output) && aligned16(grad_input) && aligned16(grad_position) && aligned16(grad_weight)) {
-        aggregation_bwd_kernel<<<warp_grid(n), GATHER_THREADS, 0, stream>>>(
-            n, nsample, t, wvec, input, position, weight, idx, grad_output, grad_input, grad_position, grad_weight);
+        if (!launch_agg_bwd_fast(lpr_of(c), nsample, n, wvec, input, position, weight, idx, grad_output, grad_input,
+                                 grad_position, grad_weight, stream))
+            aggregation_bwd_kernel<<<warp_grid(n), GATHER_THREADS, 0, stream>>>(
+                n, nsample, t, wvec, input, position, weight, idx, grad_output, grad_input, grad_position, grad_weight);
     } else {
         POB_CHECK(cudaMemsetAsync(grad_weight, 0, sizeof(float) * (size_t)n * nsample * w_c, stream));
         aggregation_bwd_scalar_kernel<<<grid_for(n * c, 256, 8), 256, 0, stream>>>(
@@ -607,7 +750,8 @@ POB_API int pob_interpolation_forward(int64_t n, int c, int k, const float* inpu
     if (n == 0) return 0;
     if (!input || !idx || !weight || !output) return POB_ERR_BAD_ARG;
     const RowTile t = row_tile(c);
-    if (t.ok && aligned16(input) && aligned16(output)) {
+    if (aligned16(input) && aligned16(output) && launch_interp_fwd_fast(lpr_of(c), n, k, input, idx, weight, output, stream)) {
+    } else if (t.ok && aligned16(input) && aligned16(output)) {
         interpolation_fwd_kernel<<<warp_grid(ceil_div(n, t.spar)), GATHER_THREADS, 0, stream>>>(n, k, t, input, idx,
                                                                                                 weight, output);
     } else {
@@ -644,6 +788,23 @@ POB_API int pob_group_xyz_forward(int64_t m, int nsample, int c, int with_xyz, c
     if (m < 0 || nsample < 1 || c < 1 || feat_dtype < 0 || feat_dtype > 2) return POB_ERR_BAD_ARG;
     if (m == 0) return 0;
     if (!feat || !idx || !output || (with_xyz && (!xyz || !new_xyz))) return POB_ERR_BAD_ARG;
+    const int lpr = lpr_of(c);
+    const bool vec_ok = lpr && ((uintptr_t)feat & 15) == 0 && aligned16(output);
+    if (vec_ok && with_xyz) {
+        int rc = -1;
+        if (feat_dtype == 0) rc = launch_group_xyz_fwd_fast<float>(lpr, m, nsample, (const float*)feat, xyz, new_xyz, idx, output, stream);
+        else if (feat_dtype == 1) rc = launch_group_xyz_fwd_fast<__half>(lpr, m, nsample, (const __half*)feat, xyz, new_xyz, idx, output, stream);
+        else rc = launch_group_xyz_fwd_fast<__nv_bfloat16>(lpr, m, nsample, (const __nv_bfloat16*)feat, xyz, new_xyz, idx, output, stream);
+        if (rc > 0) return rc;
+        if (rc == 0) { pob_count_launches(1); POB_RETURN_LAST_ERROR(); }
+    } else if (vec_ok) {  // feature-only: a masked row gather
+        const int64_t rows = m * nsample;
+        bool done;
+        if (feat_dtype == 0) done = launch_gather_fast<float, false, true>(lpr, rows, nsample, (const float*)feat, nullptr, idx, output, stream);
+        else if (feat_dtype == 1) done = launch_gather_fast<__half, false, true>(lpr, rows, nsample, (const __half*)feat, nullptr, idx, output, stream);
+        else done = launch_gather_fast<__nv_bfloat16, false, true>(lpr, rows, nsample, (const __nv_bfloat16*)feat, nullptr, idx, output, stream);
+        if (done) { pob_count_launches(1); POB_RETURN_LAST_ERROR(); }
+    }
     const unsigned grid = warp_grid(m);
     if (feat_dtype == 0)
         group_xyz_fwd_kernel<float><<<grid, GATHER_THREADS, 0, stream>>>(m, nsample, c, with_xyz, (const float*)feat, xyz,
@@ -665,6 +826,17 @@ POB_API int pob_group_xyz_backward(int64_t m, int nsample, int c, int with_xyz, 
     if (m < 0 || nsample < 1 || c < 1) return POB_ERR_BAD_ARG;
     if (m == 0) return 0;
     if (!grad_output || !idx || !grad_feat) return POB_ERR_BAD_ARG;
+    const int lpr = lpr_of(c);
+    if (lpr && aligned16(grad_feat) && aligned16(grad_output)) {
+        if (with_xyz) {
+            const int rc = launch_group_xyz_bwd_fast(lpr, m, nsample, grad_output, idx, grad_feat, stream);
+            if (rc > 0) return rc;
+            if (rc == 0) { pob_count_launches(1); POB_RETURN_LAST_ERROR(); }
+        } else if (launch_scatter_fast(lpr, m * nsample, 1.f, grad_output, idx, grad_feat, stream)) {
+            pob_count_launches(1);
+            POB_RETURN_LAST_ERROR();
+        }
+    }
     group_xyz_bwd_kernel<<<warp_grid(m), GATHER_THREADS, 0, stream>>>(m, nsample, c, with_xyz ? 3 : 0, grad_output, idx,
                                                                       grad_feat);
     pob_count_launches(1);

@@ -1,0 +1,373 @@
+// gather_fast.cuh -- compile-time-tiled versions of the gather / scatter kernels for the shapes
+// PTv1 uses (C = 4*LPR with LPR in {1,2,4,8,16,32}; nsample 8 or 16 for the reductions).
+//
+// Why a second set of kernels: the ncu capture of the run-time-tiled ones
+// (profiles/r01_gather_v1_ncu.md) showed ~43 thread-instructions per 16 bytes moved -- integer
+// address arithmetic, constant-bank reloads of the tile descriptor and per-row bounds checks --
+// and 36-110 % XU/ALU pipe utilisation, i.e. the kernels were instruction-bound, not HBM-bound.
+// Here every warp works on a TILE of R = U * (32/LPR) consecutive rows: the tile's rows of the
+// streamed operand are one contiguous span, so lane l's u-th 16-byte access is simply
+// base + u*32 + l; the only per-row integer work left is the gathered row's index.
+#pragma once
+#include "common.cuh"
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+namespace pob {
+
+constexpr int FAST_THREADS = 256;
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ float4 ldcs4(const float4* p) { return __ldcs(p); }   // streamed, evict-first
+__device__ __forceinline__ void stcs4(float4* p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 sub4(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
+    return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+__device__ __forceinline__ float4 scale4(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 xor4(float4 v, int o) {
+    return make_float4(__shfl_xor_sync(FULL, v.x, o), __shfl_xor_sync(FULL, v.y, o), __shfl_xor_sync(FULL, v.z, o),
+                       __shfl_xor_sync(FULL, v.w, o));
+}
+__device__ __forceinline__ void red_add4(float4* p, float4 v) { atomicAdd(p, v); }  // RED.E.ADD.F32x4
+
+// four consecutive channels of a feature row as f32, for f32 / f16 / bf16 storage
+template <typename T> struct Vec4Load;
+template <> struct Vec4Load<float> {
+    static __device__ __forceinline__ float4 ld(const float* base, int64_t vec) { return __ldg(reinterpret_cast<const float4*>(base) + vec); }
+};
+template <> struct Vec4Load<__half> {
+    static __device__ __forceinline__ float4 ld(const __half* base, int64_t vec) {
+        const uint2 r = __ldg(reinterpret_cast<const uint2*>(base) + vec);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+};
+template <> struct Vec4Load<__nv_bfloat16> {
+    static __device__ __forceinline__ float4 ld(const __nv_bfloat16* base, int64_t vec) {
+        const uint2 r = __ldg(reinterpret_cast<const uint2*>(base) + vec);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// out[r, :] = in[idx[r], :]                    (grouping2 forward; MASKED: idx < 0 -> zeros)
+// out[r, :] = in1[r / ns, :] - in[idx[r], :]   (SUB: subtraction forward)
+template <typename T, int LPR, int U, bool SUB, bool MASKED>
+__global__ void __launch_bounds__(FAST_THREADS)
+gather_rows_fast(int64_t rows, int ns, int ns_shift, const T* __restrict__ in, const float4* __restrict__ in1,
+                 const int* __restrict__ idx, float4* __restrict__ out) {
+    constexpr int SPAR = 32 / LPR, R = SPAR * U;
+    const int lane = threadIdx.x & 31, sub = lane / LPR, cl = lane % LPR;
+    const int64_t warp = ((int64_t)blockIdx.x * FAST_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * FAST_THREADS) >> 5;
+    const int64_t ntiles = (rows + R - 1) / R;
+    for (int64_t tile = warp; tile < ntiles; tile += nwarps) {
+        const int64_t row0 = tile * R;
+        const bool full = row0 + R <= rows;
+        const int* ip = idx + row0 + sub;
+        float4* op = out + row0 * LPR + lane;
+        int src[U];
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) src[u] = (full || row0 + u * SPAR + sub < rows) ? __ldg(ip + u * SPAR) : -1;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            v[u] = (!MASKED && full) || src[u] >= 0 ? Vec4Load<T>::ld(in, (int64_t)src[u] * LPR + cl) : zero4();
+            if (SUB) {
+                const int64_t r = row0 + u * SPAR + sub;
+                const int64_t p = ns_shift >= 0 ? (r >> ns_shift) : r / ns;
+                if (full || r < rows) v[u] = sub4(ldg4(in1 + p * LPR + cl), v[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (full || row0 + u * SPAR + sub < rows) stcs4(op + u * 32, v[u]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[n, :] = sum_s (in[idx[n,s], :] + pos[n,s,:]) * w[n,s, : % w_c]      (aggregation forward)
+// Tile = PPT whole points; the position rows of a tile are one contiguous span.
+template <int LPR, int NS>
+__global__ void __launch_bounds__(FAST_THREADS)
+aggregation_fwd_fast(int64_t n, int wvec, const float4* __restrict__ in, const float4* __restrict__ pos,
+                     const float4* __restrict__ w, const int* __restrict__ idx, float4* __restrict__ out) {
+    constexpr int SPAR = 32 / LPR;
+    constexpr int U = (NS / SPAR > 8) ? NS / SPAR : 8;  // row-slots per lane
+    constexpr int R = U * SPAR, PPT = R / NS, UPP = U / PPT;
+    static_assert(NS % SPAR == 0 && R % NS == 0, "tile must hold whole points");
+    const int lane = threadIdx.x & 31, sub = lane / LPR, cl = lane % LPR;
+    const int wv = cl & (wvec - 1);
+    const int64_t warp = ((int64_t)blockIdx.x * FAST_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * FAST_THREADS) >> 5;
+    const int64_t ntiles = (n + PPT - 1) / PPT;
+    for (int64_t tile = warp; tile < ntiles; tile += nwarps) {
+        const int64_t p0 = tile * PPT, row0 = p0 * NS;
+        const bool full = p0 + PPT <= n;
+        const int* ip = idx + row0 + sub;
+        const float4* pp = pos + row0 * LPR + lane;
+        const float4* wp = w + (row0 + sub) * wvec + wv;
+        int src[U];
+        float4 a[U], b[U], ww[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool ok = full || p0 + u / UPP < n;
+            src[u] = ok ? __ldg(ip + u * SPAR) : -1;
+            b[u] = ok ? ldcs4(pp + u * 32) : zero4();
+            ww[u] = ok ? ldg4(wp + (int64_t)u * SPAR * wvec) : zero4();
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) a[u] = src[u] >= 0 ? ldg4(in + (int64_t)src[u] * LPR + cl) : zero4();
+        float4 acc[PPT];
+#pragma unroll
+        for (int q = 0; q < PPT; q++) acc[q] = zero4();
+#pragma unroll
+        for (int u = 0; u < U; u++) acc[u / UPP] = fma4(add4(a[u], b[u]), ww[u], acc[u / UPP]);
+#pragma unroll
+        for (int q = 0; q < PPT; q++) {
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) acc[q] = add4(acc[q], xor4(acc[q], o));
+            if (sub == q % SPAR && (full || p0 + q < n)) out[(p0 + q) * LPR + cl] = acc[q];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[n, :] = sum_{i<k} in[idx[n,i], :] * w[n,i]                           (interpolation forward)
+template <int LPR, int U>
+__global__ void __launch_bounds__(FAST_THREADS)
+interpolation_fwd_fast(int64_t n, int k, const float4* __restrict__ in, const int* __restrict__ idx,
+                       const float* __restrict__ w, float4* __restrict__ out) {
+    constexpr int SPAR = 32 / LPR, R = SPAR * U;
+    const int lane = threadIdx.x & 31, sub = lane / LPR, cl = lane % LPR;
+    const int64_t warp = ((int64_t)blockIdx.x * FAST_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * FAST_THREADS) >> 5;
+    const int64_t ntiles = (n + R - 1) / R;
+    for (int64_t tile = warp; tile < ntiles; tile += nwarps) {
+        const int64_t p0 = tile * R;
+        float4 acc[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            acc[u] = zero4();
+            const int64_t p = p0 + u * SPAR + sub;
+            if (p < n) {
+                for (int i = 0; i < k; i++) {
+                    const int src = __ldg(idx + p * k + i);
+                    const float wi = __ldg(w + p * k + i);
+                    acc[u] = fma4(ldg4(in + (int64_t)src * LPR + cl), make_float4(wi, wi, wi, wi), acc[u]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (p0 + u * SPAR + sub < n) stcs4(out + p0 * LPR + u * 32 + lane, acc[u]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused grouping-with-xyz forward: out[m, s, :] = [ (xyz[idx] - new_xyz[m]) , feat[idx] ], zero
+// rows for idx < 0.  Rows are W = 3 + C floats, i.e. NOT 16-byte aligned on their own, but the
+// ns rows of one query are one contiguous span of ns*W floats: each warp assembles that span in
+// shared memory (128-bit gathers in, conflict-free scalar stores) and streams it out with
+// 128-bit stores.  Dynamic shared memory: warps_per_cta * ns * W floats.
+template <typename T, int LPR>
+__global__ void __launch_bounds__(FAST_THREADS)
+group_xyz_fwd_fast(int64_t m, int ns, const T* __restrict__ feat, const float* __restrict__ xyz,
+                   const float* __restrict__ new_xyz, const int* __restrict__ idx, float* __restrict__ out) {
+    constexpr int SPAR = 32 / LPR, C = 4 * LPR, W = C + 3;
+    extern __shared__ __align__(16) float s_tile[];
+    const int lane = threadIdx.x & 31, sub = lane / LPR, cl = lane % LPR;
+    const int per = ns * W;                       // floats per query
+    float* tile = s_tile + (threadIdx.x >> 5) * ((per + 3) & ~3);
+    const int64_t warp = ((int64_t)blockIdx.x * FAST_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * FAST_THREADS) >> 5;
+    for (int64_t q = warp; q < m; q += nwarps) {
+        const int* iq = idx + q * ns;
+        // features: SPAR rows per pass, one 16-byte gather per lane
+        for (int s0 = 0; s0 < ns; s0 += SPAR) {
+            const int s = s0 + sub;
+            if (s < ns) {
+                const int src = __ldg(iq + s);
+                const float4 v = src >= 0 ? Vec4Load<T>::ld(feat, (int64_t)src * LPR + cl) : zero4();
+                float* t = tile + s * W + 3 + 4 * cl;
+                t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+            }
+        }
+        // relative coordinates: one neighbour per lane
+        for (int s = lane; s < ns; s += 32) {
+            const int src = __ldg(iq + s);
+            float dx = 0.f, dy = 0.f, dz = 0.f;
+            if (src >= 0) {
+                dx = __fsub_rn(__ldg(xyz + (int64_t)src * 3), __ldg(new_xyz + q * 3));
+                dy = __fsub_rn(__ldg(xyz + (int64_t)src * 3 + 1), __ldg(new_xyz + q * 3 + 1));
+                dz = __fsub_rn(__ldg(xyz + (int64_t)src * 3 + 2), __ldg(new_xyz + q * 3 + 2));
+            }
+            tile[s * W] = dx; tile[s * W + 1] = dy; tile[s * W + 2] = dz;
+        }
+        __syncwarp();
+        float* o = out + q * per;
+        if ((per & 3) == 0) {   // q*per*4 bytes is then a multiple of 16
+            const float4* t4 = reinterpret_cast<const float4*>(tile);
+            float4* o4 = reinterpret_cast<float4*>(o);
+            for (int v = lane; v < per / 4; v += 32) stcs4(o4 + v, t4[v]);
+        } else {
+            for (int f = lane; f < per; f += 32) __stcs(o + f, tile[f]);
+        }
+        __syncwarp();
+    }
+}
+
+// grad_feat[idx[m,s], :] += grad_out[m, s, 3:]   for idx >= 0  (same staging, other direction)
+template <int LPR>
+__global__ void __launch_bounds__(FAST_THREADS)
+group_xyz_bwd_fast(int64_t m, int ns, const float* __restrict__ gout, const int* __restrict__ idx,
+                   float4* __restrict__ gfeat) {
+    constexpr int SPAR = 32 / LPR, C = 4 * LPR, W = C + 3;
+    extern __shared__ __align__(16) float s_tile[];
+    const int lane = threadIdx.x & 31, sub = lane / LPR, cl = lane % LPR;
+    const int per = ns * W;
+    float* tile = s_tile + (threadIdx.x >> 5) * ((per + 3) & ~3);
+    const int64_t warp = ((int64_t)blockIdx.x * FAST_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * FAST_THREADS) >> 5;
+    for (int64_t q = warp; q < m; q += nwarps) {
+        const float* g = gout + q * per;
+        if ((per & 3) == 0) {
+            const float4* g4 = reinterpret_cast<const float4*>(g);
+            float4* t4 = reinterpret_cast<float4*>(tile);
+            for (int v = lane; v < per / 4; v += 32) t4[v] = ldcs4(g4 + v);
+        } else {
+            for (int f = lane; f < per; f += 32) tile[f] = __ldcs(g + f);
+        }
+        __syncwarp();
+        const int* iq = idx + q * ns;
+        for (int s0 = 0; s0 < ns; s0 += SPAR) {
+            const int s = s0 + sub;
+            if (s < ns) {
+                const int dst = __ldg(iq + s);
+                if (dst >= 0) {
+                    const float* t = tile + s * W + 3 + 4 * cl;
+                    red_add4(gfeat + (int64_t)dst * LPR + cl, make_float4(t[0], t[1], t[2], t[3]));
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gin[idx[r], :] += sign * gout[r, :]          (grouping2 backward, subtraction backward w.r.t. input2)
+template <int LPR, int U>
+__global__ void __launch_bounds__(FAST_THREADS)
+scatter_rows_fast(int64_t rows, float sign, const float4* __restrict__ gout, const int* __restrict__ idx,
+                  float4* __restrict__ gin) {
+    constexpr int SPAR = 32 / LPR, R = SPAR * U;
+    const int lane = threadIdx.x & 31, sub = lane / LPR, cl = lane % LPR;
+    const int64_t warp = ((int64_t)blockIdx.x * FAST_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * FAST_THREADS) >> 5;
+    const int64_t ntiles = (rows + R - 1) / R;
+    for (int64_t tile = warp; tile < ntiles; tile += nwarps) {
+        const int64_t row0 = tile * R;
+        const bool full = row0 + R <= rows;
+        int dst[U];
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool ok = full || row0 + u * SPAR + sub < rows;
+            dst[u] = ok ? __ldg(idx + row0 + u * SPAR + sub) : -1;
+            v[u] = ok ? ldcs4(gout + row0 * LPR + u * 32 + lane) : zero4();
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (dst[u] >= 0) red_add4(gin + (int64_t)dst[u] * LPR + cl, scale4(v[u], sign));
+    }
+}
+
+// g1[n, :] = sum_s gout[n, s, :]               (subtraction backward w.r.t. input1)
+template <int LPR, int NS>
+__global__ void __launch_bounds__(FAST_THREADS)
+reduce_neighbours_fast(int64_t n, const float4* __restrict__ gout, float4* __restrict__ g1) {
+    constexpr int SPAR = 32 / LPR;
+    constexpr int U = (NS / SPAR > 8) ? NS / SPAR : 8;
+    constexpr int R = U * SPAR, PPT = R / NS, UPP = U / PPT;
+    static_assert(NS % SPAR == 0 && R % NS == 0, "tile must hold whole points");
+    const int lane = threadIdx.x & 31, sub = lane / LPR, cl = lane % LPR;
+    const int64_t warp = ((int64_t)blockIdx.x * FAST_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * FAST_THREADS) >> 5;
+    const int64_t ntiles = (n + PPT - 1) / PPT;
+    for (int64_t tile = warp; tile < ntiles; tile += nwarps) {
+        const int64_t p0 = tile * PPT;
+        const bool full = p0 + PPT <= n;
+        const float4* gp = gout + p0 * NS * LPR + lane;
+        float4 b[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) b[u] = (full || p0 + u / UPP < n) ? ldcs4(gp + u * 32) : zero4();
+        float4 acc[PPT];
+#pragma unroll
+        for (int q = 0; q < PPT; q++) acc[q] = zero4();
+#pragma unroll
+        for (int u = 0; u < U; u++) acc[u / UPP] = add4(acc[u / UPP], b[u]);
+#pragma unroll
+        for (int q = 0; q < PPT; q++) {
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) acc[q] = add4(acc[q], xor4(acc[q], o));
+            if (sub == q % SPAR && (full || p0 + q < n)) g1[(p0 + q) * LPR + cl] = acc[q];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// aggregation backward: grad_in (vector atomics), grad_pos (streamed), grad_w (shuffle reduction)
+template <int LPR, int NS>
+__global__ void __launch_bounds__(FAST_THREADS)
+aggregation_bwd_fast(int64_t n, int wvec, const float4* __restrict__ in, const float4* __restrict__ pos,
+                     const float4* __restrict__ w, const int* __restrict__ idx, const float4* __restrict__ gout,
+                     float4* __restrict__ gin, float4* __restrict__ gpos, float4* __restrict__ gw) {
+    constexpr int SPAR = 32 / LPR;
+    constexpr int U = (NS / SPAR > 4) ? NS / SPAR : 4;
+    constexpr int R = U * SPAR, PPT = R / NS, UPP = U / PPT;
+    static_assert(NS % SPAR == 0 && R % NS == 0, "tile must hold whole points");
+    const int lane = threadIdx.x & 31, sub = lane / LPR, cl = lane % LPR;
+    const int wv = cl & (wvec - 1);
+    const int64_t warp = ((int64_t)blockIdx.x * FAST_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * FAST_THREADS) >> 5;
+    const int64_t ntiles = (n + PPT - 1) / PPT;
+    for (int64_t tile = warp; tile < ntiles; tile += nwarps) {
+        const int64_t p0 = tile * PPT, row0 = p0 * NS;
+        const bool full = p0 + PPT <= n;
+        float4 g[PPT];
+#pragma unroll
+        for (int q = 0; q < PPT; q++) g[q] = (full || p0 + q < n) ? ldg4(gout + (p0 + q) * LPR + cl) : zero4();
+        int src[U];
+        float4 a[U], b[U], ww[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool ok = full || p0 + u / UPP < n;
+            src[u] = ok ? __ldg(idx + row0 + u * SPAR + sub) : -1;
+            b[u] = ok ? ldcs4(pos + row0 * LPR + u * 32 + lane) : zero4();
+            ww[u] = ok ? ldg4(w + (row0 + u * SPAR + sub) * wvec + wv) : zero4();
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) a[u] = src[u] >= 0 ? ldg4(in + (int64_t)src[u] * LPR + cl) : zero4();
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool ok = full || p0 + u / UPP < n;
+            const float4 gq = g[u / UPP];
+            const float4 gwv = mul4(gq, ww[u]);
+            if (ok) stcs4(gpos + row0 * LPR + u * 32 + lane, gwv);
+            if (src[u] >= 0) red_add4(gin + (int64_t)src[u] * LPR + cl, gwv);
+            float4 part = mul4(gq, add4(a[u], b[u]));
+            // lanes of one row whose channel vectors agree modulo wvec share a weight vector
+            for (int o = wvec; o < LPR; o <<= 1) part = add4(part, xor4(part, o));
+            if (ok && cl < wvec) gw[(row0 + u * SPAR + sub) * wvec + cl] = part;
+        }
+    }
+}
+
+}  // namespace pob

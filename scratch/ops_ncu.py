@@ -1,0 +1,24 @@
+import sys, torch
+sys.path.insert(0, '.')
+from pointcloudpdf_b200 import synthetic as S
+import pointops
+dev = torch.device('cuda:0')
+N, ns, Cc = 80000, 8, 32
+b = S.s3dis_batch([N], seed=2025)
+xyz = b['coord'].to(dev); off = b['offset'].to(dev)
+idx, _ = pointops.knn_query(ns, xyz, off)
+g = torch.Generator(device=dev).manual_seed(0)
+mk = lambda *shape: torch.randn(*shape, device=dev, generator=g)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+f = mk(N, Cc).requires_grad_(True); f2 = mk(N, Cc).requires_grad_(True)
+pos = mk(N, ns, Cc).requires_grad_(True); w = mk(N, ns, Cc // 8).requires_grad_(True)
+for rep in range(2):
+    flush.zero_(); o1 = pointops.grouping(idx, f, xyz, xyz, True)
+    flush.zero_(); o1.backward(mk(N, ns, Cc + 3))
+    flush.zero_(); o2 = pointops.grouping2(f, idx)
+    flush.zero_(); o2.backward(mk(N, ns, Cc))
+    flush.zero_(); o3 = pointops.subtraction(f, f2, idx)
+    flush.zero_(); o3.backward(mk(N, ns, Cc))
+    flush.zero_(); o4 = pointops.aggregation(f, pos, w, idx)
+    flush.zero_(); o4.backward(mk(N, Cc))
+torch.cuda.synchronize()
