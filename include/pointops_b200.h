@@ -141,6 +141,10 @@ int pob_group_xyz_forward(int64_t m, int nsample, int c, int with_xyz, const voi
                           cudaStream_t stream);
 int pob_group_xyz_backward(int64_t m, int nsample, int c, int with_xyz, const float* grad_output, const int* idx,
                            float* grad_feat, cudaStream_t stream);
+/* The coordinate half alone: output (m, nsample, 3) = xyz[idx] - new_xyz[m], zeros for idx < 0
+ * (functions/grouping.py:49-57); no gradient (the reference gives xyz none).                    */
+int pob_group_relxyz_forward(int64_t m, int nsample, const float* xyz, const float* new_xyz, const int* idx,
+                             float* output, cudaStream_t stream);
 
 /* ------------------------------------------ fused open-set scoring (additive entry point) --
  * One pass over logits (n, K) [+ conf (n)] replacing

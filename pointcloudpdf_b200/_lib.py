@@ -40,6 +40,7 @@ SIGNATURES = {
     "pob_interpolation_backward": (I, [L, I, I, P, P, P, P, P]),
     "pob_group_xyz_forward": (I, [L, I, I, I, P, I, P, P, P, P, P]),
     "pob_group_xyz_backward": (I, [L, I, I, I, P, P, P, P]),
+    "pob_group_relxyz_forward": (I, [L, I, P, P, P, P, P]),
     "pob_score_workspace_bytes": (Z, [I]),
     "pob_score_fused": (I, [L, I, I, P, P, P, F, P, P, P, P, P, P, P, P, P, Z, P]),
 }

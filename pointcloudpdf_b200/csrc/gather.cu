@@ -15,6 +15,7 @@
 // The fast paths need C % 4 == 0 with C/4 a power of two (or a multiple of 32) -- every PTv1
 // width (32..512) qualifies; other shapes take the scalar kernels at the bottom, which are
 // still CUDA: there is no CPU fallback anywhere.
+#include <cstdlib>
 #include "common.cuh"
 #include "gather_fast.cuh"
 #include <cuda_fp16.h>
@@ -356,6 +357,24 @@ group_xyz_bwd_kernel(int64_t m, int ns, int c, int coff, const float* __restrict
     }
 }
 
+// out[m, s, :] = (xyz[idx[m,s]] - new_xyz[m]) * [idx >= 0]   (the coordinate half of
+// pointops.grouping(with_xyz=True), functions/grouping.py:49-57, on its own)
+__global__ void __launch_bounds__(256)
+group_relxyz_kernel(int64_t rows, int ns, int ns_shift, const float* __restrict__ xyz,
+                    const float* __restrict__ new_xyz, const int* __restrict__ idx, float* __restrict__ out) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int src = __ldg(idx + r);
+        const int64_t q = ns_shift >= 0 ? (r >> ns_shift) : r / ns;
+        float dx = 0.f, dy = 0.f, dz = 0.f;
+        if (src >= 0) {
+            dx = __fsub_rn(__ldg(xyz + (int64_t)src * 3), __ldg(new_xyz + q * 3));
+            dy = __fsub_rn(__ldg(xyz + (int64_t)src * 3 + 1), __ldg(new_xyz + q * 3 + 1));
+            dz = __fsub_rn(__ldg(xyz + (int64_t)src * 3 + 2), __ldg(new_xyz + q * 3 + 2));
+        }
+        out[r * 3] = dx; out[r * 3 + 1] = dy; out[r * 3 + 2] = dz;
+    }
+}
+
 // ------------------------------------------------------- scalar kernels (any shape) --
 __global__ void gather_rows_scalar_kernel(int64_t total, int ns, int c, int sub, const float* __restrict__ in,
                                           const float* __restrict__ in1, const int* __restrict__ idx,
@@ -471,6 +490,8 @@ static inline int shift_of(int v) {  // log2 for powers of two, else -1
     while ((1 << s) < v) s++;
     return s;
 }
+static const bool USE_PIPE = getenv("POINTOPS_B200_NO_PIPE") == nullptr;
+
 static inline unsigned fast_grid(int64_t warps_needed) {
     const int64_t ctas = ceil_div(warps_needed, FAST_THREADS / 32);
     const int64_t cap = (int64_t)sm_count() * 16;
@@ -519,9 +540,48 @@ static bool launch_reduce_fast(int lpr, int ns, int64_t n, const float* gout, fl
     return true;
 }
 
+// pipelined (bulk-async) aggregation over the full tiles; returns the number of points it covered
+template <int L, int NS>
+static int64_t launch_agg_fwd_pipe(int64_t n, int wvec, const float* in, const float* pos, const float* w,
+                                   const int* idx, float* out, cudaStream_t stream, int* err) {
+    constexpr int SPAR = 32 / L;
+    constexpr int U = (NS / SPAR > 8) ? NS / SPAR : 8;
+    constexpr int R = U * SPAR, PPT = R / NS;
+    const int64_t ntiles = n / PPT;
+    const int64_t ctas = (int64_t)sm_count() * 2;
+    if (ntiles < ctas * (FAST_THREADS / 32) * 3) return 0;  // too little work to fill the rings
+    const size_t stage = (size_t)R * L * 16 + (size_t)R * wvec * 16 + (((size_t)R * 4 + 15) & ~(size_t)15);
+    const size_t smem = (FAST_THREADS / 32) * (pipe::STAGES * stage + 64);
+    if (smem > 115000) return 0;  // two CTAs per SM must fit in 227 KB
+    auto kern = aggregation_fwd_pipe<L, NS>;
+    static size_t configured = 0;  // per instantiation: the attribute only ever needs to grow
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { *err = (int)e; return 0; }
+        configured = smem;
+    }
+    kern<<<(unsigned)ctas, FAST_THREADS, smem, stream>>>(ntiles, wvec, (const float4*)in, (const float4*)pos,
+                                                         (const float4*)w, idx, (float4*)out);
+    pob_count_launches(1);
+    return ntiles * PPT;
+}
+
 static bool launch_agg_fwd_fast(int lpr, int ns, int64_t n, int wvec, const float* in, const float* pos, const float* w,
                                 const int* idx, float* out, cudaStream_t stream) {
     if (!ns_tiled(lpr, ns)) return false;
+    if (USE_PIPE) {
+        int err = 0;
+        int64_t done = 0;
+#define M(L) { if (ns == 8) { if constexpr (tile_ok<L, 8>()) done = launch_agg_fwd_pipe<L, 8>(n, wvec, in, pos, w, idx, out, stream, &err); } \
+               else { if constexpr (tile_ok<L, 16>()) done = launch_agg_fwd_pipe<L, 16>(n, wvec, in, pos, w, idx, out, stream, &err); } }
+        POB_LPR_SWITCH(lpr, M)
+#undef M
+        if (done >= n) return true;
+        if (done > 0) {  // remainder (< one tile of points) through the plain tiled kernel
+            in = in; pos += done * ns * (int64_t)lpr * 4; w += done * ns * (int64_t)wvec * 4; idx += done * ns;
+            out += done * (int64_t)lpr * 4; n -= done;
+        }
+    }
 #define M(L) { if (ns == 8) { if constexpr (tile_ok<L, 8>()) { constexpr int U = ((8 / (32 / L)) > 8) ? 8 / (32 / L) : 8; \
             aggregation_fwd_fast<L, 8><<<fast_grid(ceil_div(n, (U * (32 / L)) / 8)), FAST_THREADS, 0, stream>>>( \
                 n, wvec, (const float4*)in, (const float4*)pos, (const float4*)w, idx, (float4*)out); } } \
@@ -839,6 +899,21 @@ POB_API int pob_group_xyz_backward(int64_t m, int nsample, int c, int with_xyz, 
     }
     group_xyz_bwd_kernel<<<warp_grid(m), GATHER_THREADS, 0, stream>>>(m, nsample, c, with_xyz ? 3 : 0, grad_output, idx,
                                                                       grad_feat);
+    pob_count_launches(1);
+    POB_RETURN_LAST_ERROR();
+}
+
+// Coordinate half of pointops.grouping(with_xyz=True) alone: output (m, nsample, 3) f32 =
+// xyz[idx] - new_xyz[m], zero rows for idx < 0.  Lets a caller keep the gathered features in
+// their own 16-byte-aligned tensor instead of the 3+C interleaved one.
+POB_API int pob_group_relxyz_forward(int64_t m, int nsample, const float* xyz, const float* new_xyz, const int* idx,
+                                     float* output, cudaStream_t stream) {
+    if (m < 0 || nsample < 1) return POB_ERR_BAD_ARG;
+    if (m == 0) return 0;
+    if (!xyz || !new_xyz || !idx || !output) return POB_ERR_BAD_ARG;
+    const int64_t rows = m * nsample;
+    group_relxyz_kernel<<<grid_for(rows, 256, 8), 256, 0, stream>>>(rows, nsample, shift_of(nsample), xyz, new_xyz, idx,
+                                                                   output);
     pob_count_launches(1);
     POB_RETURN_LAST_ERROR();
 }

@@ -370,4 +370,136 @@ aggregation_bwd_fast(int64_t n, int wvec, const float4* __restrict__ in, const f
     }
 }
 
+
+// =============================================================================================
+// Bulk-async (TMA) pipelined variants for the kernels whose dominant operand is a contiguous
+// stream (position / weight / index tiles of aggregation).  The compile-time-tiled kernels above
+// are latency-bound (ncu: 18-25 long-scoreboard stalls per issue, DRAM at 36-50 %): a warp loads
+// a tile, waits, gathers, waits, stores, and only occupancy overlaps those waits.  Here every
+// warp runs its own 3-stage ring in shared memory: lane 0 issues cp.async.bulk copies of the next
+// tiles' contiguous spans (one instruction per span, completion counted by an mbarrier), so
+// ~13 KB per warp / ~200 KB per SM are in flight while the warp gathers and reduces the current
+// tile.  Persistent grid: 2 CTAs per SM.
+namespace pipe {
+
+__device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+constexpr int STAGES = 3;
+
+}  // namespace pipe
+
+// out[n, :] = sum_s (in[idx[n,s], :] + pos[n,s,:]) * w[n,s, : % w_c]  over `ntiles` FULL tiles
+template <int LPR, int NS>
+__global__ void __launch_bounds__(FAST_THREADS)
+aggregation_fwd_pipe(int64_t ntiles, int wvec, const float4* __restrict__ in, const float4* __restrict__ pos,
+                     const float4* __restrict__ w, const int* __restrict__ idx, float4* __restrict__ out) {
+    using namespace pipe;
+    constexpr int SPAR = 32 / LPR;
+    constexpr int U = (NS / SPAR > 8) ? NS / SPAR : 8;
+    constexpr int R = U * SPAR, PPT = R / NS, UPP = U / PPT;
+    static_assert(NS % SPAR == 0 && R % NS == 0, "tile must hold whole points");
+    constexpr unsigned PB = R * LPR * 16, IB = R * 4;
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    const unsigned WB = (unsigned)(R * wvec * 16);
+    const unsigned stage_bytes = PB + WB + ((IB + 15u) & ~15u);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, sub = lane / LPR, cl = lane % LPR;
+    const int wv = cl & (wvec - 1);
+    unsigned char* my = s_raw + (size_t)wid * (STAGES * stage_bytes + 64);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(my + STAGES * stage_bytes);
+    const int64_t warp = ((int64_t)blockIdx.x * FAST_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * FAST_THREADS) >> 5;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) bar_init(s32(bars + s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int s, int64_t tile) {  // lane 0 only
+        const int64_t row0 = tile * R;
+        unsigned char* st = my + s * stage_bytes;
+        const unsigned bar = s32(bars + s);
+        bar_expect(bar, PB + WB + IB);
+        bulk_g2s(s32(st), pos + row0 * LPR, PB, bar);
+        bulk_g2s(s32(st + PB), w + row0 * wvec, WB, bar);
+        bulk_g2s(s32(st + PB + WB), idx + row0, IB, bar);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) {
+            const int64_t t = warp + (int64_t)s * nwarps;
+            if (t < ntiles) issue(s, t);
+        }
+    }
+    // k-th tile of this warp lives in stage k % STAGES, completed phase parity (k / STAGES) & 1.
+    // The gathers of tile k+1 are issued before tile k is reduced, so their L2/DRAM latency hides
+    // behind the arithmetic and the stage hand-over of tile k.
+    auto gather = [&](int k, float4 (&a)[U]) {
+        const int s = k % STAGES;
+        bar_wait(s32(bars + s), (unsigned)(k / STAGES) & 1u);
+        const int* si = reinterpret_cast<const int*>(my + s * stage_bytes + PB + WB);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int src = si[u * SPAR + sub];
+            a[u] = src >= 0 ? ldg4(in + (int64_t)src * LPR + cl) : zero4();
+        }
+    };
+    float4 a_cur[U], a_next[U];
+    if (warp < ntiles) gather(0, a_cur);
+    int k = 0;
+    for (int64_t tile = warp; tile < ntiles; tile += nwarps, k++) {
+        const int s = k % STAGES;
+        const bool more = tile + nwarps < ntiles;
+        if (more) gather(k + 1, a_next);
+        const unsigned char* st = my + s * stage_bytes;
+        const float4* sp = reinterpret_cast<const float4*>(st);
+        const float4* sw = reinterpret_cast<const float4*>(st + PB);
+        float4 acc[PPT];
+#pragma unroll
+        for (int q = 0; q < PPT; q++) acc[q] = zero4();
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const float4 b = sp[u * 32 + lane];
+            const float4 ww = sw[(u * SPAR + sub) * wvec + wv];
+            acc[u / UPP] = fma4(add4(a_cur[u], b), ww, acc[u / UPP]);
+        }
+        __syncwarp();  // everyone is done reading this stage
+        if (lane == 0) {
+            const int64_t nt = tile + (int64_t)STAGES * nwarps;
+            if (nt < ntiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(s, nt);
+            }
+        }
+        const int64_t p0 = tile * PPT;
+#pragma unroll
+        for (int q = 0; q < PPT; q++) {
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) acc[q] = add4(acc[q], xor4(acc[q], o));
+            if (sub == q % SPAR) out[(p0 + q) * LPR + cl] = acc[q];
+        }
+        if (more) {
+#pragma unroll
+            for (int u = 0; u < U; u++) a_cur[u] = a_next[u];
+        }
+    }
+}
+
 }  // namespace pob

@@ -7,7 +7,7 @@ queryandgroup; libs/pointops2/functions/pointops.py:34,56,964) are provided as a
 """
 from .query import knn_query, ball_query, random_ball_query, KNNQuery
 from .sampling import farthest_point_sampling, FarthestPointSampling
-from .grouping import grouping, grouping2, Grouping
+from .grouping import grouping, grouping2, Grouping, grouping_split
 from .interpolation import interpolation, interpolation2, Interpolation
 from .subtraction import subtraction, Subtraction
 from .aggregation import aggregation, Aggregation

@@ -96,3 +96,20 @@ def grouping(idx, feat, xyz, new_xyz=None, with_xyz=False):
     if feat.shape[0] != xyz.shape[0]:
         raise ValueError("feat and xyz must have the same number of rows")
     return _GroupXYZ.apply(feat, idx, xyz, new_xyz, bool(with_xyz))
+
+
+def grouping_split(idx, feat, xyz, new_xyz=None):
+    """Same values as ``grouping(idx, feat, xyz, new_xyz, with_xyz=True)`` but as two tensors,
+    ``(rel_xyz (m, ns, 3), grouped_feat (m, ns, c))``: both stay contiguous and 16-byte aligned,
+    so callers that slice the concatenated form apart again (PointTransformerLayer,
+    point_transformer_seg.py:64) skip the interleave and the strided re-reads.  Additive API."""
+    if new_xyz is None:
+        new_xyz = xyz
+    grouped = grouping(idx, feat, xyz, new_xyz, with_xyz=False)
+    C.require(new_xyz, "new_xyz", torch.float32, 2, 3)
+    m, nsample = idx.shape
+    rel = torch.empty((m, nsample, 3), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.run("pob_group_relxyz_forward", m, nsample, _lib.ptr(xyz), _lib.ptr(new_xyz), _lib.ptr(idx), _lib.ptr(rel),
+                 _lib.current_stream(xyz.device), alg_bytes=4 * (3 * xyz.shape[0] + 3 * m + m * nsample + 3 * m * nsample))
+    return rel, grouped

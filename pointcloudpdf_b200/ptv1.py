@@ -92,8 +92,11 @@ class PointTransformerLayer(nn.Module):
             idx = cloud.knn(self.nsample)
         else:  # the reference's literal sequence: kNN inside every layer
             idx, _ = pointops.knn_query(self.nsample, p, o)
-        g = pointops.grouping(idx, x_k, p, p, with_xyz=True)  # (n, ns, 3 + c)
-        p_r, x_kg = g[:, :, 0:3], g[:, :, 3:]
+        if self.fused:  # same values as the interleaved tensor, kept as two aligned ones
+            p_r, x_kg = pointops.grouping_split(idx, x_k, p, p)
+        else:
+            g = pointops.grouping(idx, x_k, p, p, with_xyz=True)  # (n, ns, 3 + c)
+            p_r, x_kg = g[:, :, 0:3], g[:, :, 3:]
         p_r = self.linear_p(p_r)                                # (n, ns, out)
         n, ns, _ = p_r.shape
         # the reference reduces p_r over "(i j) -> j" with j = mid_planes; i == 1 here: the identity
