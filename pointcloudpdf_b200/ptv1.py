@@ -33,25 +33,48 @@ from . import pointops
 from .pointops import _common as C
 
 
+class Level:
+    """Coordinate-only state of one resolution level, computed ahead of the features on a side
+    stream (PointTransformerSeg.geometry): self-kNN index, and -- towards the next coarser level --
+    the FPS selection, the cross kNN index and the 3-NN interpolation index/weights."""
+
+    __slots__ = ("p", "o", "o_host", "knn", "knn_ev", "down", "down_ev", "coarser")
+
+    def __init__(self, p, o, o_host):
+        self.p, self.o, self.o_host = p, o, list(o_host)
+        self.knn, self.knn_ev = {}, None
+        self.down, self.down_ev, self.coarser = None, None, None
+
+
+def _wait(ev):
+    if ev is not None:
+        torch.cuda.current_stream().wait_event(ev)
+
+
 class Cloud:
     """One resolution level: coordinates, features, cumulative offsets (device + host copy) and
     the self-kNN index shared by every block of the level."""
 
-    __slots__ = ("p", "x", "o", "o_host", "_knn")
+    __slots__ = ("p", "x", "o", "o_host", "_knn", "level")
 
-    def __init__(self, p, x, o, o_host):
+    def __init__(self, p, x, o, o_host, level=None):
         self.p, self.x, self.o, self.o_host = p, x, o, list(o_host)
         self._knn = {}
+        self.level = level
 
     def with_feat(self, x) -> "Cloud":
-        c = Cloud(self.p, x, self.o, self.o_host)
+        c = Cloud(self.p, x, self.o, self.o_host, self.level)
         c._knn = self._knn
         return c
 
     def knn(self, nsample: int) -> torch.Tensor:
         idx = self._knn.get(nsample)
         if idx is None:
-            idx, _ = pointops.knn_query(nsample, self.p, self.o)
+            if self.level is not None and nsample in self.level.knn:
+                _wait(self.level.knn_ev)
+                idx = self.level.knn[nsample]
+            else:
+                idx, _ = pointops.knn_query(nsample, self.p, self.o)
             self._knn[nsample] = idx
         return idx
 
@@ -111,6 +134,15 @@ class PointTransformerLayer(nn.Module):
         return out.reshape(n, self.out_planes)
 
 
+def strided_offsets(o_host: Sequence[int], stride: int) -> List[int]:
+    """Cumulative per-scene sample counts n_b // stride (point_transformer_seg.py:99-103), on the host."""
+    out, acc = [], 0
+    for n_b in C.scene_sizes(o_host):
+        acc += n_b // stride
+        out.append(acc)
+    return out
+
+
 class TransitionDown(nn.Module):
     def __init__(self, in_planes, out_planes, stride=1, nsample=16):
         super().__init__()
@@ -127,23 +159,26 @@ class TransitionDown(nn.Module):
         if self.stride == 1:
             return cloud.with_feat(self.relu(self.bn(self.linear(cloud.x))))
         p, x, o = cloud.p, cloud.x, cloud.o
-        # per-scene sample counts n_b // stride, cumulative (point_transformer_seg.py:99-103), on the host
-        sizes = C.scene_sizes(cloud.o_host)
-        n_o_host, acc = [], 0
-        for s in sizes:
-            acc += s // self.stride
-            n_o_host.append(acc)
-        n_o = torch.tensor(n_o_host, dtype=torch.int32).to(p.device, non_blocking=True)
-        C.register_host_offset(n_o, n_o_host)
-        C.register_host_offset(o, cloud.o_host)
-        idx = pointops.farthest_point_sampling(p, o, n_o)          # (m)
-        n_p = p[idx.long(), :]                                     # (m, 3)
-        g, _ = pointops.knn_query_and_group(x, p, offset=o, new_xyz=n_p, new_offset=n_o, nsample=self.nsample,
-                                            with_xyz=True)        # (m, ns, 3 + c)
+        lvl = cloud.level
+        if lvl is not None and lvl.down is not None:   # computed ahead on the geometry stream
+            _wait(lvl.down_ev)
+            n_p, n_o, n_o_host, cross_idx = lvl.down["n_p"], lvl.down["n_o"], lvl.down["n_o_host"], lvl.down["cross"]
+            g = pointops.grouping(cross_idx, x, p, n_p, with_xyz=True)
+            nxt = lvl.coarser
+        else:
+            n_o_host = strided_offsets(cloud.o_host, self.stride)
+            n_o = torch.tensor(n_o_host, dtype=torch.int32).to(p.device, non_blocking=True)
+            C.register_host_offset(n_o, n_o_host)
+            C.register_host_offset(o, cloud.o_host)
+            idx = pointops.farthest_point_sampling(p, o, n_o)          # (m)
+            n_p = p[idx.long(), :]                                     # (m, 3)
+            g, _ = pointops.knn_query_and_group(x, p, offset=o, new_xyz=n_p, new_offset=n_o, nsample=self.nsample,
+                                                with_xyz=True)        # (m, ns, 3 + c)
+            nxt = None
         m, ns, w = g.shape
         y = self.relu(self.bn(self.linear(g).view(m * ns, -1)))    # BN over (m, ns) per channel, no transpose
         y = y.view(m, ns, -1).max(dim=1)[0]                        # MaxPool1d(nsample)
-        return Cloud(n_p, y, n_o, n_o_host)
+        return Cloud(n_p, y, n_o, n_o_host, nxt)
 
 
 class TransitionUp(nn.Module):
@@ -174,7 +209,14 @@ class TransitionUp(nn.Module):
                 sums = torch.zeros((b, x.shape[1]), dtype=x.dtype, device=x.device).index_add_(0, batch, x)
                 tiled = self.linear2(sums / counts.to(x.dtype).unsqueeze(1))[batch]
             return self.linear1(torch.cat((x, tiled), 1))
-        up = pointops.interpolation(coarse.p, fine.p, self.linear2(coarse.x), coarse.o, fine.o)
+        feat = self.linear2(coarse.x)
+        lvl = fine.level
+        if lvl is not None and lvl.down is not None and coarse.level is lvl.coarser and coarse.level is not None:
+            _wait(lvl.down_ev)
+            from .pointops.interpolation import _InterpolateRows
+            up = _InterpolateRows.apply(feat.float().contiguous(), lvl.down["up_idx"], lvl.down["up_w"])
+        else:
+            up = pointops.interpolation(coarse.p, fine.p, feat, coarse.o, fine.o)
         return self.linear1(fine.x) + up
 
 
@@ -217,6 +259,9 @@ class PointTransformerSeg(nn.Module):
         self.cls = nn.Sequential(nn.Linear(planes[0], planes[0]), nn.BatchNorm1d(planes[0]), nn.ReLU(inplace=True),
                                  nn.Linear(planes[0], num_classes))
         self.taps = None  # filled per forward: what the reference's ModelHook would capture
+        self.overlap_geometry = True  # coordinate-only work on a side stream (fused path only)
+        self._geo_stream = None
+        self._all_fused = True
 
     def _make_enc(self, block, planes, blocks, share_planes=8, stride=1, nsample=16):
         layers = [TransitionDown(self.in_planes, planes * block.expansion, stride, nsample)]
@@ -236,16 +281,67 @@ class PointTransformerSeg(nn.Module):
         for m in self.modules():
             if isinstance(m, PointTransformerLayer):
                 m.fused = bool(fused)
+        self._all_fused = bool(fused)
         return self
 
-    def forward(self, data_dict, offset_host: Optional[Sequence[int]] = None):
+    @torch.no_grad()
+    def geometry(self, p0, o0, offset_host, stream=None) -> List[Level]:
+        """Everything that depends on coordinates only -- 4 FPS, 5 self-kNN, 4 cross-kNN, 4 three-NN
+        with weights -- issued on `stream` so that it overlaps the feature path (FPS is a serial,
+        16-SM kernel; the linears run on the other SMs meanwhile).  Each item carries the event
+        the feature path waits on.  Results are bit-identical to computing them inline."""
+        main = torch.cuda.current_stream()
+        stream = stream if stream is not None else main
+        strides = [m[0].stride for m in (self.enc1, self.enc2, self.enc3, self.enc4, self.enc5)]
+        nsamples = [m[0].nsample for m in (self.enc1, self.enc2, self.enc3, self.enc4, self.enc5)]
+        stream.wait_stream(main)
+        levels: List[Level] = []
+        keep = []
+        with torch.cuda.stream(stream):
+            C.register_host_offset(o0, offset_host)
+            lvl = Level(p0, o0, offset_host)
+            for s in range(5):
+                levels.append(lvl)
+                lvl.knn[nsamples[s]] = pointops.knn_query(nsamples[s], lvl.p, lvl.o)[0]
+                lvl.knn_ev = torch.cuda.Event()
+                lvl.knn_ev.record(stream)
+                keep.append(lvl.knn[nsamples[s]])
+                if s == 4:
+                    break
+                n_o_host = strided_offsets(lvl.o_host, strides[s + 1])
+                n_o = torch.tensor(n_o_host, dtype=torch.int32).to(lvl.p.device, non_blocking=True)
+                C.register_host_offset(n_o, n_o_host)
+                sel = pointops.farthest_point_sampling(lvl.p, lvl.o, n_o)
+                n_p = lvl.p[sel.long(), :]
+                cross = pointops.knn_query(nsamples[s + 1], lvl.p, lvl.o, n_p, n_o)[0]
+                up_idx, _, up_w = C.cached_knn(3, n_p, n_o, lvl.p, lvl.o, want_weight=True)
+                up_idx = torch.where(up_idx < 0, up_idx + n_p.shape[0], up_idx)  # quirk C6, as pointops.interpolation
+                lvl.down = dict(n_p=n_p, n_o=n_o, n_o_host=n_o_host, cross=cross, up_idx=up_idx, up_w=up_w)
+                lvl.down_ev = torch.cuda.Event()
+                lvl.down_ev.record(stream)
+                keep += [n_p, n_o, cross, up_idx, up_w]
+                lvl.coarser = Level(n_p, n_o, n_o_host)
+                lvl = lvl.coarser
+        if stream is not main:
+            for t in keep:
+                t.record_stream(main)  # consumed by kernels on the main stream
+        return levels
+
+    def forward(self, data_dict, offset_host: Optional[Sequence[int]] = None, geometry: Optional[List[Level]] = None):
         p0, x0 = data_dict["coord"], data_dict["feat"]
         o0 = data_dict["offset"].int()
         if offset_host is None:
             offset_host = C.host_offset(o0)
         else:
             C.register_host_offset(o0, offset_host)
-        c1 = self.enc1(Cloud(p0, x0, o0, offset_host))
+        level0 = None
+        if geometry is not None:      # computed ahead by the caller (OpenSegPTv1.infer_stream)
+            level0 = geometry[0]
+        elif self.overlap_geometry and p0.is_cuda and self._all_fused:
+            if self._geo_stream is None:
+                self._geo_stream = torch.cuda.Stream(device=p0.device)
+            level0 = self.geometry(p0.contiguous(), o0, offset_host, self._geo_stream)[0]
+        c1 = self.enc1(Cloud(p0, x0, o0, offset_host, level0))
         c2 = self.enc2(c1)
         c3 = self.enc3(c2)
         c4 = self.enc4(c3)
@@ -256,6 +352,8 @@ class PointTransformerSeg(nn.Module):
         d2 = self.dec2[1:](c2.with_feat(self.dec2[0](c2, d3)))
         d1 = self.dec1[1:](c1.with_feat(self.dec1[0](c1, d2)))
         self.taps = dict(enc=[c1, c2, c3, c4, c5], dec=[d1, d2, d3, d4, d5])
+        if level0 is not None and geometry is None:
+            torch.cuda.current_stream().wait_stream(self._geo_stream)
         return self.cls(d1.x)
 
 
@@ -312,10 +410,11 @@ class OpenSegPTv1(nn.Module):
         self.backbone = PointTransformerSeg(Bottleneck, list(blocks), in_channels=in_channels, num_classes=num_classes)
         self.method = method
         self.recognizer = PTRecognizer() if method == "pdf" else None
+        self._streams = []
 
-    def forward(self, data_dict, offset_host=None):
+    def forward(self, data_dict, offset_host=None, geometry=None):
         from .scoring import fused_scores
-        logits = self.backbone(data_dict, offset_host).float().contiguous()
+        logits = self.backbone(data_dict, offset_host, geometry).float().contiguous()
         if self.method == "pdf":
             conf = self.recognizer(self.backbone.taps).float().contiguous()
             score = fused_scores(logits, conf, want=("pdf_score",))["pdf_score"]
@@ -333,3 +432,61 @@ class OpenSegPTv1(nn.Module):
                  offset=offset.to(dev, non_blocking=True))
         out = self.forward(d, offset_host)
         return out["score"].cpu(), out["seg_logits"].argmax(-1).to(torch.int32).cpu()
+
+    @torch.no_grad()
+    def infer_stream(self, rooms, depth: int = 2, device=None):
+        """Serve a sequence of rooms ``(coord, feat, offset)`` (host tensors, pinned recommended),
+        yielding ``(score, pred)`` host tensors per room, in order.
+
+        Same arithmetic as calling ``infer`` room by room; what changes is the schedule: the
+        host->device copy and the coordinate-only work (FPS, kNN) of the next ``depth`` rooms run
+        ahead on their own streams while the feature path of the current room runs on the main
+        stream, and the host only blocks on a room's result after the next room has been queued.
+        FPS is a serial 16-SM kernel, so this keeps the other 132 SMs busy."""
+        dev = device if device is not None else next(self.parameters()).device
+        if len(self._streams) < depth:
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+        main = torch.cuda.current_stream(dev)
+        rooms = list(rooms)
+        prepared = {}
+
+        def prepare(i):
+            coord, feat, offset = rooms[i]
+            st = self._streams[i % depth]
+            # run-ahead is bounded: geometry() makes `st` wait for what the main stream has queued
+            # so far, i.e. room i's coordinate work starts once room i - depth has left the GPU
+            pointops.clear_caches()  # nothing is reusable across rooms; drop what the last ones pinned
+            offset_host = offset.tolist()
+            with torch.cuda.stream(st):
+                d = dict(coord=coord.to(dev, non_blocking=True), feat=feat.to(dev, non_blocking=True),
+                         offset=offset.to(dev, non_blocking=True).int())
+                ev = torch.cuda.Event()
+                ev.record(st)
+            for t in d.values():
+                t.record_stream(main)
+            levels = self.backbone.geometry(d["coord"], d["offset"], offset_host, st)
+            prepared[i] = (d, offset_host, levels, ev)
+
+        for i in range(min(depth, len(rooms))):
+            prepare(i)
+        pending = None
+        for i in range(len(rooms)):
+            d, offset_host, levels, ev = prepared.pop(i)
+            main.wait_event(ev)
+            out = self.forward(d, offset_host, levels)
+            n_i = out["score"].shape[0]
+            score = torch.empty((n_i,), dtype=torch.float32, pin_memory=True)
+            pred = torch.empty((n_i,), dtype=torch.int32, pin_memory=True)
+            score.copy_(out["score"], non_blocking=True)
+            pred.copy_(out["seg_logits"].argmax(-1).to(torch.int32), non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            if i + depth < len(rooms):
+                prepare(i + depth)
+            if pending is not None:
+                pending[0].synchronize()
+                yield pending[1], pending[2]
+            pending = (done, score, pred)
+        if pending is not None:
+            pending[0].synchronize()
+            yield pending[1], pending[2]
