@@ -130,6 +130,17 @@ def test_fps_bit_exact(cuda, oracle, sizes, stride):
     assert torch.equal(out.cpu(), ref)
 
 
+def test_fps_full_size_80k_to_20k(cuda, oracle):
+    """BASELINE's stage-1 size: 19 999 dependent iterations, 16-CTA cluster, cell-ordered pruning.
+    Exact f32 ties between running minima do occur at this size; the contract (lowest index) decides."""
+    import pointops
+    xyz, offset = make_cloud([80000], 2026, "room")
+    new_offset = torch.tensor([20000], dtype=torch.int32)
+    ref = oracle.farthest_point_sampling(xyz, offset, new_offset)
+    out = pointops.farthest_point_sampling(xyz.to(cuda), offset.to(cuda), new_offset.to(cuda))
+    assert torch.equal(out.cpu(), ref)
+
+
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
 def test_fps_every_cluster_size_same_result(cuda, oracle, cluster):
     from pointcloudpdf_b200 import _lib
