@@ -146,6 +146,44 @@ int pob_group_xyz_backward(int64_t m, int nsample, int c, int with_xyz, const fl
 int pob_group_relxyz_forward(int64_t m, int nsample, const float* xyz, const float* new_xyz, const int* idx,
                              float* output, cudaStream_t stream);
 
+/* --------------------- inference form of PointTransformerLayer (additive entry points) ------
+ * The caller of the operators above, pointcept/models/point_transformer/point_transformer_seg.py:48-81,
+ * spends its time between the q/k/v linears and the layer output in ~16 eager kernels per block
+ * (two kNN-group gathers, linear_p, the relation k_j - q_i + p_r, linear_w, softmax over the
+ * neighbours, the einsum aggregation).  With every BatchNorm in eval mode that chain is one kernel:
+ *   h   = relu(A (xyz[j] - xyz[i]) + c)            Linear(3,3) + BN folded   (j = idx[i,s]; 0 if j < 0)
+ *   p_r = Wp h + bp                                 Linear(3, C)
+ *   t   = relu(aw * (k[j] - q[i] + p_r) + bw)       first BN of linear_w as an affine map
+ *   u   = relu(W1 t + b1)                           Linear(C, C/8) + BN folded
+ *   l   = W2 u + b2 ;  w = softmax over s of l      Linear(C/8, C/8)
+ *   out[i,c] = sum_s (v[j,c] + p_r[c]) * w[s, c % (C/8)]   ( then relu(oa * out + ob) if out_affine: bn2 )
+ * params is ONE packed f32 block, 16-byte aligned, pob_pt_layer_param_floats(c, w_c) floats:
+ *   A[9] c[3] pad[4] | wx[C] wy[C] wz[C] bp[C] aw[C] bw[C] oa[C] ob[C] | W1[w_c][C] | b1[w_c] |
+ *   W2^T[w_c][w_c] (W2T[o][o'] = W2[o'][o]) | b2[w_c]
+ * q, k, v (n, c) with row strides ldq / ldk / ldv floats (column blocks of one (n, 3c) GEMM output are
+ * fine); out (n, c) with row stride ldo.  Supported: c in {32,64,128,256,512}, w_c = c/8, nsample in {8,16};
+ * anything else returns POB_ERR_UNSUPPORTED (callers then run the unfused operator sequence).      */
+int64_t pob_pt_layer_param_floats(int c, int w_c);
+int pob_pt_layer_forward(int64_t n, int nsample, int c, int w_c, const float* q, int64_t ldq, const float* k,
+                         int64_t ldk, const float* v, int64_t ldv, const float* xyz, const int* idx,
+                         const float* params, int out_affine, float* out, int64_t ldo, cudaStream_t stream);
+/* out = relu?(x * scale + shift + residual) over (rows, c); scale, shift (c) and residual (rows, c) may be
+ * NULL; in place allowed.  The BN / skip / ReLU tail of Bottleneck (point_transformer_seg.py:188-195).  */
+int pob_affine_act(int64_t rows, int c, const float* x, const float* scale, const float* shift,
+                   const float* residual, int relu, float* out, cudaStream_t stream);
+/* TransitionDown (point_transformer_seg.py:106-119) with its Linear(3 + C, C') split by linearity:
+ * z (n, c) = feat @ W[:, 3:]^T computed by the caller on the UNGATHERED points (cuBLAS), wxyz (c, 3) =
+ * W[:, :3]; out (m, c) = max_s relu(scale * (z[idx[m,s]] + wxyz (xyz[idx[m,s]] - new_xyz[m])) + shift)
+ * = gather + coordinate columns + BatchNorm(eval) + ReLU + MaxPool1d(nsample) in one pass; idx < 0
+ * contributes a zero grouped row (pointops.grouping's mask).  c % 4 == 0.                           */
+int pob_transition_down_pool(int64_t m, int nsample, int c, const float* z, const float* xyz, const float* new_xyz,
+                             const int* idx, const float* wxyz, const float* scale, const float* shift,
+                             float* out, cudaStream_t stream);
+/* output = base + interpolation_forward(input, idx, weight): TransitionUp's skip connection folded in
+ * (point_transformer_seg.py:168-170); base may be NULL.                                             */
+int pob_interpolation_add_forward(int64_t n, int c, int k, const float* input, const int* idx, const float* weight,
+                                  const float* base, float* output, cudaStream_t stream);
+
 /* ------------------------------------------ fused open-set scoring (additive entry point) --
  * One pass over logits (n, K) [+ conf (n)] replacing
  *   MaxProbability msp / ml  (pointcept/recognizers/max_probability/max_probability_v1m1_base.py:17-29),

@@ -41,6 +41,11 @@ SIGNATURES = {
     "pob_group_xyz_forward": (I, [L, I, I, I, P, I, P, P, P, P, P]),
     "pob_group_xyz_backward": (I, [L, I, I, I, P, P, P, P]),
     "pob_group_relxyz_forward": (I, [L, I, P, P, P, P, P]),
+    "pob_pt_layer_param_floats": (L, [I, I]),
+    "pob_pt_layer_forward": (I, [L, I, I, I, P, L, P, L, P, L, P, P, P, I, P, L, P]),
+    "pob_affine_act": (I, [L, I, P, P, P, P, I, P, P]),
+    "pob_transition_down_pool": (I, [L, I, I, P, P, P, P, P, P, P, P, P]),
+    "pob_interpolation_add_forward": (I, [L, I, I, P, P, P, P, P, P]),
     "pob_score_workspace_bytes": (Z, [I]),
     "pob_score_fused": (I, [L, I, I, P, P, P, F, P, P, P, P, P, P, P, P, P, Z, P]),
 }

@@ -319,7 +319,7 @@ static int launch_cluster(const void* kernel, int b, int C, int threads, size_t 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (C > 8) POB_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    if (smem > 48 * 1024) POB_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 32 * 1024) POB_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // static smem counts against the 48 KB default too
     POB_CHECK(cudaLaunchKernelExC(&cfg, kernel, args));
     pob_count_launches(1);
     return 0;

@@ -31,6 +31,79 @@ import torch.nn.functional as F
 
 from . import pointops
 from .pointops import _common as C
+from .pointops import fused as FZ
+
+
+# ------------------------------------------------------------- frozen (inference) form ----
+# In eval mode under torch.no_grad() every BatchNorm is a per-channel affine map, so the eager glue
+# between the cuBLAS linears folds away:
+#   Linear -> BN -> ReLU                      = one cublasLt GEMM with bias + ReLU epilogue
+#   q, k, v linears                           = one GEMM on concatenated weights
+#   gathers, linear_p, relation, linear_w, softmax, aggregation, bn2, ReLU = pob_pt_layer_forward
+#   TransitionDown's Linear(3+C, C') on the grouped tensor = GEMM on the UNGATHERED points (linearity)
+#     + pob_transition_down_pool (gather, coordinate columns, BN, ReLU, max over neighbours)
+#   TransitionUp's interpolation + skip      = pob_interpolation_add_forward
+# ~900 kernel launches per 80k-point room become ~170; the modules, their parameters and their
+# state_dict are untouched -- the folded tensors are a cache, dropped on train() / .to() /
+# load_state_dict() and rebuilt lazily (call invalidate_frozen() after editing weights in place).
+
+def _bn_affine(bn: nn.BatchNorm1d):
+    a = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+    b = bn.bias.detach().double() - bn.running_mean.detach().double() * a
+    return a, b
+
+
+def _fold(linear: nn.Linear, bn: Optional[nn.BatchNorm1d]):
+    """(W', b') in f32 with bn(linear(x)) == x @ W'.T + b' in eval mode (folded in f64)."""
+    W = linear.weight.detach().double()
+    b = linear.bias.detach().double() if linear.bias is not None else torch.zeros(W.shape[0], dtype=torch.float64, device=W.device)
+    if bn is not None:
+        a, sh = _bn_affine(bn)
+        W, b = W * a[:, None], b * a + sh
+    return W.float().contiguous(), b.float().contiguous()
+
+
+def _f32(t):
+    return t.detach().float().contiguous()
+
+
+class _Freezable:
+    """Mixin: cache of folded inference tensors, dropped whenever the parameters may have changed."""
+    _frozen = None
+    use_frozen = True
+
+    def train(self, mode: bool = True):
+        self._frozen = None
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._frozen = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._frozen = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _can_freeze(self, x: torch.Tensor) -> bool:
+        return (self.use_frozen and not self.training and not torch.is_grad_enabled() and x.is_cuda
+                and x.dtype == torch.float32)
+
+    def frozen(self):
+        f = self._frozen
+        if f is None:
+            with torch.no_grad():
+                f = self._frozen = self._freeze()
+        return f
+
+
+def invalidate_frozen(module: nn.Module) -> None:
+    for m in module.modules():
+        if isinstance(m, _Freezable):
+            m._frozen = None
+
+
+def _linear_act(f, x):  # relu(x @ W'.T + b') in one cublasLt call
+    return torch._addmm_activation(f[1], x, f[0])
 
 
 class Level:
@@ -143,7 +216,7 @@ def strided_offsets(o_host: Sequence[int], stride: int) -> List[int]:
     return out
 
 
-class TransitionDown(nn.Module):
+class TransitionDown(_Freezable, nn.Module):
     def __init__(self, in_planes, out_planes, stride=1, nsample=16):
         super().__init__()
         self.stride, self.nsample = stride, nsample
@@ -155,15 +228,25 @@ class TransitionDown(nn.Module):
         self.bn = nn.BatchNorm1d(out_planes)
         self.relu = nn.ReLU(inplace=True)
 
-    def forward(self, cloud: Cloud) -> Cloud:
+    def _freeze(self):
         if self.stride == 1:
+            W, b = _fold(self.linear, self.bn)
+            return dict(lin=(W.t(), b))
+        W = self.linear.weight.detach()
+        a, sh = _bn_affine(self.bn)
+        return dict(wxyz=_f32(W[:, :3]), wfeat_t=_f32(W[:, 3:]).t(), scale=a.float().contiguous(), shift=sh.float().contiguous())
+
+    def forward(self, cloud: Cloud) -> Cloud:
+        frozen = self._can_freeze(cloud.x)
+        if self.stride == 1:
+            if frozen:
+                return cloud.with_feat(_linear_act(self.frozen()["lin"], cloud.x))
             return cloud.with_feat(self.relu(self.bn(self.linear(cloud.x))))
         p, x, o = cloud.p, cloud.x, cloud.o
         lvl = cloud.level
         if lvl is not None and lvl.down is not None:   # computed ahead on the geometry stream
             _wait(lvl.down_ev)
             n_p, n_o, n_o_host, cross_idx = lvl.down["n_p"], lvl.down["n_o"], lvl.down["n_o_host"], lvl.down["cross"]
-            g = pointops.grouping(cross_idx, x, p, n_p, with_xyz=True)
             nxt = lvl.coarser
         else:
             n_o_host = strided_offsets(cloud.o_host, self.stride)
@@ -172,16 +255,21 @@ class TransitionDown(nn.Module):
             C.register_host_offset(o, cloud.o_host)
             idx = pointops.farthest_point_sampling(p, o, n_o)          # (m)
             n_p = p[idx.long(), :]                                     # (m, 3)
-            g, _ = pointops.knn_query_and_group(x, p, offset=o, new_xyz=n_p, new_offset=n_o, nsample=self.nsample,
-                                                with_xyz=True)        # (m, ns, 3 + c)
+            cross_idx, _ = pointops.knn_query(self.nsample, p, o, n_p, n_o)
             nxt = None
+        if frozen and x.shape[1] % 4 == 0 and self.linear.out_features % 4 == 0:
+            f = self.frozen()
+            z = torch.mm(x, f["wfeat_t"])                              # (n, c'): the GEMM on ungathered points
+            y = FZ.transition_down_pool(z, p, n_p, cross_idx, f["wxyz"], f["scale"], f["shift"])
+            return Cloud(n_p, y, n_o, n_o_host, nxt)
+        g = pointops.grouping(cross_idx, x, p, n_p, with_xyz=True)     # (m, ns, 3 + c)
         m, ns, w = g.shape
         y = self.relu(self.bn(self.linear(g).view(m * ns, -1)))    # BN over (m, ns) per channel, no transpose
         y = y.view(m, ns, -1).max(dim=1)[0]                        # MaxPool1d(nsample)
         return Cloud(n_p, y, n_o, n_o_host, nxt)
 
 
-class TransitionUp(nn.Module):
+class TransitionUp(_Freezable, nn.Module):
     def __init__(self, in_planes, out_planes=None):
         super().__init__()
         if out_planes is None:
@@ -194,12 +282,28 @@ class TransitionUp(nn.Module):
             self.linear2 = nn.Sequential(nn.Linear(in_planes, out_planes), nn.BatchNorm1d(out_planes),
                                          nn.ReLU(inplace=True))
 
+    def _freeze(self):
+        W1, b1 = _fold(self.linear1[0], self.linear1[1])
+        if isinstance(self.linear2[1], nn.BatchNorm1d):
+            W2, b2 = _fold(self.linear2[0], self.linear2[1])
+            return dict(l1=(W1.t(), b1), l2=(W2.t(), b2))
+        c = W1.shape[0]   # head: linear1 takes cat(x, tiled scene mean); linear2 is Linear + ReLU
+        W2, b2 = _fold(self.linear2[0], None)
+        return dict(l1a_t=W1[:, :c].contiguous().t(), l1b_t=W1[:, c:].contiguous().t(), b1=b1, l2=(W2.t(), b2))
+
     def forward(self, fine: Cloud, coarse: Optional[Cloud] = None) -> torch.Tensor:
+        frozen = self._can_freeze(fine.x)
         if coarse is None:
             # head: concatenate every point with its scene's mean feature (:152-164), segmented
             x = fine.x
             sizes = C.scene_sizes(fine.o_host)
             b = len(sizes)
+            if b == 1 and frozen:
+                # cat(x, tiled) @ W.T = x @ Wa.T + (mean-feature row) @ Wb.T: the second term is a bias
+                f = self.frozen()
+                t = _linear_act(f["l2"], x.mean(0, keepdim=True))
+                bias = torch.addmm(f["b1"], t, f["l1b_t"]).view(-1)
+                return torch._addmm_activation(bias, x, f["l1a_t"])
             if b == 1:
                 mean = x.sum(0, keepdim=True) / sizes[0]
                 tiled = self.linear2(mean).expand(x.shape[0], -1)
@@ -209,9 +313,22 @@ class TransitionUp(nn.Module):
                 sums = torch.zeros((b, x.shape[1]), dtype=x.dtype, device=x.device).index_add_(0, batch, x)
                 tiled = self.linear2(sums / counts.to(x.dtype).unsqueeze(1))[batch]
             return self.linear1(torch.cat((x, tiled), 1))
-        feat = self.linear2(coarse.x)
         lvl = fine.level
-        if lvl is not None and lvl.down is not None and coarse.level is lvl.coarser and coarse.level is not None:
+        ahead = lvl is not None and lvl.down is not None and coarse.level is lvl.coarser and coarse.level is not None
+        if frozen and fine.x.shape[1] % 4 == 0:
+            f = self.frozen()
+            feat = _linear_act(f["l2"], coarse.x)
+            base = _linear_act(f["l1"], fine.x)
+            if ahead:
+                _wait(lvl.down_ev)
+                up_idx, up_w = lvl.down["up_idx"], lvl.down["up_w"]
+            else:
+                from .pointops.interpolation import _neighbours_and_weights, _wrap_placeholders
+                up_idx, up_w = _neighbours_and_weights(coarse.p, fine.p, coarse.o, fine.o, 3)
+                up_idx = _wrap_placeholders(up_idx, feat.shape[0])
+            return FZ.interpolation_add(feat, up_idx, up_w, base=base, inplace=True)
+        feat = self.linear2(coarse.x)
+        if ahead:
             _wait(lvl.down_ev)
             from .pointops.interpolation import _InterpolateRows
             up = _InterpolateRows.apply(feat.float().contiguous(), lvl.down["up_idx"], lvl.down["up_w"])
@@ -220,7 +337,7 @@ class TransitionUp(nn.Module):
         return self.linear1(fine.x) + up
 
 
-class Bottleneck(nn.Module):
+class Bottleneck(_Freezable, nn.Module):
     expansion = 1
 
     def __init__(self, in_planes, planes, share_planes=8, nsample=16):
@@ -233,8 +350,35 @@ class Bottleneck(nn.Module):
         self.bn3 = nn.BatchNorm1d(planes * self.expansion)
         self.relu = nn.ReLU(inplace=True)
 
+    def _freeze(self):
+        t = self.transformer
+        W1, b1 = _fold(self.linear1, self.bn1)
+        Wqkv = torch.cat([t.linear_q.weight, t.linear_k.weight, t.linear_v.weight]).detach().float().contiguous()
+        bqkv = torch.cat([t.linear_q.bias, t.linear_k.bias, t.linear_v.bias]).detach().float().contiguous()
+        A, cvec = _fold(t.linear_p[0], t.linear_p[1])
+        aw, bw = _bn_affine(t.linear_w[0])
+        w1, b1w = _fold(t.linear_w[2], t.linear_w[3])
+        oa, ob = _bn_affine(self.bn2)
+        params = FZ.pack_pt_layer_params(A, cvec, t.linear_p[3].weight, t.linear_p[3].bias, aw, bw, w1, b1w,
+                                         t.linear_w[5].weight, t.linear_w[5].bias, oa, ob)
+        W3, b3 = _fold(self.linear3, self.bn3)
+        return dict(l1=(W1.t(), b1), wqkv_t=Wqkv.t(), bqkv=bqkv, params=params, w3_t=W3.t(), b3=b3)
+
+    def _frozen_ok(self, x) -> bool:
+        t = self.transformer
+        return (self._can_freeze(x) and t.fused and t.mid_planes == t.out_planes
+                and FZ.pt_layer_supported(t.out_planes, t.share_planes, t.nsample))
+
     def forward(self, cloud: Cloud) -> Cloud:
         identity = cloud.x
+        if self._frozen_ok(identity):
+            f = self.frozen()
+            c = self.transformer.out_planes
+            qkv = torch.addmm(f["bqkv"], _linear_act(f["l1"], identity), f["wqkv_t"])        # (n, 3c)
+            y = FZ.pt_layer_forward(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], cloud.p, cloud.knn(self.transformer.nsample),
+                                    f["params"], out_affine=True)                             # ... bn2 + relu
+            z = torch.addmm(identity, y, f["w3_t"])                                           # skip + linear3 (bn3 scale folded)
+            return cloud.with_feat(FZ.affine_act(z, None, f["b3"], None, relu=True, inplace=True))
         x = self.relu(self.bn1(self.linear1(cloud.x)))
         x = self.relu(self.bn2(self.transformer(cloud.with_feat(x))))
         x = self.bn3(self.linear3(x))
@@ -242,7 +386,7 @@ class Bottleneck(nn.Module):
         return cloud.with_feat(x)
 
 
-class PointTransformerSeg(nn.Module):
+class PointTransformerSeg(_Freezable, nn.Module):
     """Encoder-decoder of point_transformer_seg.py:198-306; ``forward(data_dict)`` takes the
     reference's dict (coord, feat, offset) and returns per-point logits."""
 
@@ -281,6 +425,8 @@ class PointTransformerSeg(nn.Module):
         for m in self.modules():
             if isinstance(m, PointTransformerLayer):
                 m.fused = bool(fused)
+            if isinstance(m, _Freezable):
+                m.use_frozen = bool(fused)
         self._all_fused = bool(fused)
         return self
 
@@ -354,7 +500,15 @@ class PointTransformerSeg(nn.Module):
         self.taps = dict(enc=[c1, c2, c3, c4, c5], dec=[d1, d2, d3, d4, d5])
         if level0 is not None and geometry is None:
             torch.cuda.current_stream().wait_stream(self._geo_stream)
+        if self._can_freeze(d1.x):
+            f = self.frozen()
+            return torch.addmm(f["out"][1], _linear_act(f["hid"], d1.x), f["out"][0])
         return self.cls(d1.x)
+
+    def _freeze(self):
+        W, b = _fold(self.cls[0], self.cls[1])
+        Wo, bo = _fold(self.cls[3], None)
+        return dict(hid=(W.t(), b), out=(Wo.t(), bo))
 
 
 class PointTransformerSeg26(PointTransformerSeg):
@@ -372,7 +526,7 @@ class PointTransformerSeg50(PointTransformerSeg):
         super().__init__(Bottleneck, [1, 2, 3, 5, 2], **kwargs)
 
 
-class PTRecognizer(nn.Module):
+class PTRecognizer(_Freezable, nn.Module):
     """PDF U-decoder (recognizers/recognizer_model/pt_v1.py:8-44): five TransitionUp over the
     backbone's hooked encoder/decoder activations, then a confidence head -> conf (n, 1)."""
 
@@ -396,7 +550,15 @@ class PTRecognizer(nn.Module):
         r3 = self.dec3(d3, c4.with_feat(r4))
         r2 = self.dec2(d2, c3.with_feat(r3))
         r1 = self.dec1(d1, c2.with_feat(r2))
+        if self._can_freeze(r1):
+            f = self.frozen()
+            return torch.addmm(f["out"][1], _linear_act(f["hid"], r1), f["out"][0])
         return self.confidence(r1)
+
+    def _freeze(self):
+        W, b = _fold(self.confidence[0], self.confidence[1])
+        Wo, bo = _fold(self.confidence[3], None)
+        return dict(hid=(W.t(), b), out=(Wo.t(), bo))
 
 
 class OpenSegPTv1(nn.Module):
@@ -417,11 +579,13 @@ class OpenSegPTv1(nn.Module):
         logits = self.backbone(data_dict, offset_host, geometry).float().contiguous()
         if self.method == "pdf":
             conf = self.recognizer(self.backbone.taps).float().contiguous()
-            score = fused_scores(logits, conf, want=("pdf_score",))["pdf_score"]
+            r = fused_scores(logits, conf, want=("pdf_score", "pred"))
+            score = r["pdf_score"]
         else:
             key = "msp_score" if self.method == "msp" else "ml_score"
-            score = fused_scores(logits, want=(key,))[key]
-        return dict(seg_logits=logits, score=score)
+            r = fused_scores(logits, want=(key, "pred"))
+            score = r[key]
+        return dict(seg_logits=logits, score=score, pred=r["pred"])  # pred = argmax of the logits (first maximum), i32
 
     @torch.no_grad()
     def infer(self, coord: torch.Tensor, feat: torch.Tensor, offset: torch.Tensor, device=None):
@@ -431,7 +595,7 @@ class OpenSegPTv1(nn.Module):
         d = dict(coord=coord.to(dev, non_blocking=True), feat=feat.to(dev, non_blocking=True),
                  offset=offset.to(dev, non_blocking=True))
         out = self.forward(d, offset_host)
-        return out["score"].cpu(), out["seg_logits"].argmax(-1).to(torch.int32).cpu()
+        return out["score"].cpu(), out["pred"].cpu()
 
     @torch.no_grad()
     def infer_stream(self, rooms, depth: int = 2, device=None):
@@ -478,7 +642,7 @@ class OpenSegPTv1(nn.Module):
             score = torch.empty((n_i,), dtype=torch.float32, pin_memory=True)
             pred = torch.empty((n_i,), dtype=torch.int32, pin_memory=True)
             score.copy_(out["score"], non_blocking=True)
-            pred.copy_(out["seg_logits"].argmax(-1).to(torch.int32), non_blocking=True)
+            pred.copy_(out["pred"], non_blocking=True)
             done = torch.cuda.Event()
             done.record(main)
             if i + depth < len(rooms):
