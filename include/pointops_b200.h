@@ -83,6 +83,9 @@ int pob_knn_query_bruteforce(int64_t m, int nsample, int b, const float* xyz, co
  * xyz / offset, with its n (rows of xyz) and cell_pts; the kernel then walks the points in cell
  * order and skips, exactly, every warp whose bounding box is out of the new sample's reach.
  * The result is bit-identical with or without it.                                              */
+/* Diagnostics: device pointer to 2 x uint64 {rounds, samples} that FPS launches accumulate into
+ * (mean samples accepted per cluster-wide exchange = samples / rounds), or NULL to switch it off. */
+int pob_fps_set_stats(void* device_u64x2);
 int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, const int* offset,
                                 const int* new_offset, float* tmp, int* idx, int cluster_hint,
                                 const void* grid_workspace, int64_t n, float cell_pts, cudaStream_t stream);

@@ -27,6 +27,8 @@
 #include "common.cuh"
 #include "grid.cuh"
 #include <cooperative_groups.h>
+#include <cstdlib>
+#include <cstring>
 
 namespace cg = cooperative_groups;
 
@@ -247,6 +249,267 @@ fps_cluster_kernel(const float* __restrict__ xyz, const int* __restrict__ offset
     if (C > 1) cluster.sync();  // nobody leaves while a peer may still be writing into its shared memory
 }
 
+// ---------------------------------------------------------------------------------------------
+// fps_chain_kernel: the same register-resident layout, but SEVERAL samples per synchronisation
+// round.  The serial chain of FPS is "argmax, update, argmax, ...", one cluster-wide exchange
+// (~260 ns) per sample.  Observation: every exchange already tells every CTA the maxima of ALL
+// groups (CTAs; warps when the cluster is one CTA).  Sort them by the key (value desc, index asc):
+// a_1 > a_2 > ... (distinct groups).  a_1 is the next sample.  a_2 is the sample after it iff
+//   (i)  a_1 does not lower a_2's own min-distance:  d2(a_2, a_1) >= tmp[a_2], and
+//   (ii) the group of a_1, once a_1 is applied, holds nothing above a_2:  V_1 < tmp[a_2],
+// because every other group's maximum was <= a_2 and min-distances only ever decrease.  In general
+// a_{j+1} follows a_1..a_j iff it is lowered by none of them and V_i < tmp[a_{j+1}] for all i <= j,
+// where V_i is ANY upper bound of group i's maximum after its own candidate a_i has been applied.
+// Each warp keeps, next to its maximum e_w, the exact value V_w = max_p min(tmp_p, d2(p, top_w))
+// (a dry run against its own top point, redone only when the warp's points changed); a CTA
+// publishes E = max_w e_w (warp w*) and V = max(V_w*, second largest e_w).  One exchange then
+// yields a whole accepted prefix a_1..a_L (L <= 8), all CTAs derive the same L from the same 16
+// messages, apply the L samples (same exact pruning), and go round again.  The emitted index
+// sequence is IDENTICAL to one-sample-at-a-time FPS (ties: the strict tests fall back to L = 1).
+// Measured on S3DIS-shaped rooms: see profiles/ (mean accepted chain length and ns per sample).
+constexpr int FPS_KMAX = 8;
+
+struct __align__(16) FpsEntry {  // one group's candidate, 32 bytes
+    unsigned bits;               // float bits of the group's maximum min-distance
+    int idx;                     // global (original) index of the point attaining it (lowest among ties)
+    float x, y, z;               // its coordinates
+    unsigned vbits;              // float bits of V: bound on the group's maximum once this point is a sample
+    int pad0, pad1;
+};
+
+__device__ __forceinline__ unsigned long long fps_key(unsigned bits, int idx) {
+    // orders like (value desc, index asc) under unsigned 64-bit '>'
+    return ((unsigned long long)bits << 32) | (unsigned)(~idx);
+}
+
+template <int P, int T>
+__global__ void __launch_bounds__(T, 1)
+fps_chain_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
+                 const SceneGrid* __restrict__ scenes, const int* __restrict__ cell_start,
+                 const float4* __restrict__ sorted, int* __restrict__ idx, unsigned long long* __restrict__ stats) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    int rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int scene = blockIdx.x / C;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = T / 32;
+    constexpr int NG = FPS_MAX_CLUSTER;  // group slots ranked per round (unused ones stay zero)
+    static_assert(NW <= NG, "group entries are ranked 16 at a time");
+
+    const int s_n = scene == 0 ? 0 : offset[scene - 1], e_n = offset[scene];
+    const int s_m = scene == 0 ? 0 : new_offset[scene - 1], e_m = new_offset[scene];
+
+    extern __shared__ float s_xyz[];  // [3][T*P]
+    __shared__ __align__(16) FpsEntry s_warp[2][NG];          // warp entries by round parity (slots >= NW stay zero)
+    __shared__ __align__(16) FpsEntry s_msg[2][NG];           // CTA entries from the peers, by round parity
+    __shared__ __align__(16) FpsEntry s_sorted[NW][NG];       // per warp: the candidates in key order
+    __shared__ __align__(8) unsigned long long s_bar[2];
+
+    if (e_m <= s_m || e_n <= s_n) return;  // uniform over the cluster
+    const int n = e_n - s_n;
+    const int total = e_m - s_m;
+
+    const bool in_cells = scenes != nullptr && scenes[scene].use_grid;
+    float px[P], py[P], pz[P], pt[P];
+    int pi[P];
+    float blo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, bhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    bool box_ok = true;
+    const int sbase = in_cells ? __ldg(cell_start + scenes[scene].cell_base) : 0;
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        const int pos = in_cells ? ((rank * NW + warp) * P + p) * 32 + lane : p * (C * T) + rank * T + tid;
+        if (pos < n) {
+            if (in_cells) {
+                const float4 v = __ldg(sorted + sbase + pos);
+                px[p] = v.x; py[p] = v.y; pz[p] = v.z; pi[p] = __float_as_int(v.w);
+            } else {
+                const int i = s_n + pos;
+                px[p] = __ldg(xyz + (int64_t)i * 3); py[p] = __ldg(xyz + (int64_t)i * 3 + 1); pz[p] = __ldg(xyz + (int64_t)i * 3 + 2);
+                pi[p] = i;
+            }
+            pt[p] = PLACEHOLDER_D2;
+            box_ok = box_ok && isfinite(px[p]) && isfinite(py[p]) && isfinite(pz[p]);
+            blo[0] = fminf(blo[0], px[p]); bhi[0] = fmaxf(bhi[0], px[p]);
+            blo[1] = fminf(blo[1], py[p]); bhi[1] = fmaxf(bhi[1], py[p]);
+            blo[2] = fminf(blo[2], pz[p]); bhi[2] = fmaxf(bhi[2], pz[p]);
+        } else {
+            px[p] = py[p] = pz[p] = 0.f;
+            pt[p] = -1.f;  // never a maximum: fminf keeps it at -1
+            pi[p] = INT_MAX;
+        }
+        const int slot = (warp * P + p) * 32 + lane;
+        s_xyz[slot] = px[p]; s_xyz[T * P + slot] = py[p]; s_xyz[2 * T * P + slot] = pz[p];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            blo[a] = fminf(blo[a], __shfl_xor_sync(FULL, blo[a], o));
+            bhi[a] = fmaxf(bhi[a], __shfl_xor_sync(FULL, bhi[a], o));
+        }
+    }
+    const bool prune = in_cells && __all_sync(FULL, box_ok);
+
+    // zero the group slots (a zero entry ranks below every real candidate and is never accepted)
+    for (int i = tid; i < 2 * NG * (int)(sizeof(FpsEntry) / 16); i += T) {
+        reinterpret_cast<float4*>(s_warp)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<float4*>(s_msg)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const bool writer = rank == 0 && warp == 0;
+    const unsigned bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]);
+    unsigned rslot0 = 0, rslot1 = 0, rbar0 = 0, rbar1 = 0;
+    if (writer && lane == 0) idx[s_m] = s_n;  // sampling_cuda_kernel.cu:39
+    if (C > 1) {
+        if (tid == 0) {
+            mbar_init(bar0, 1);
+            mbar_init(bar1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(bar0, C * (int)sizeof(FpsEntry));
+            mbar_expect_tx(bar1, C * (int)sizeof(FpsEntry));
+        }
+        if (warp == 0 && lane < C) {  // lane l talks to CTA l
+            rslot0 = mapa_u32(smem_u32(&s_msg[0][rank]), lane);
+            rslot1 = mapa_u32(smem_u32(&s_msg[1][rank]), lane);
+            rbar0 = mapa_u32(bar0, lane);
+            rbar1 = mapa_u32(bar1, lane);
+        }
+        cluster.sync();
+    } else {
+        __syncthreads();
+    }
+
+    // lane <-> candidate pair (pa < pb), pb-major: (0,1) (0,2) (1,2) (0,3) ...; 28 pairs for 8 candidates
+    int pb = 1, pbase = 0;
+    while (pbase + pb <= lane) { pbase += pb; pb++; }
+    const int pa = lane - pbase;
+    FpsEntry* my_sorted = s_sorted[warp];
+
+    // the accepted, not yet applied samples: lane j < L holds a_j.  First one: the scene's first point.
+    FpsEntry E;
+    E.bits = __float_as_uint(PLACEHOLDER_D2); E.idx = s_n;
+    E.x = __ldg(xyz + (int64_t)s_n * 3); E.y = __ldg(xyz + (int64_t)s_n * 3 + 1); E.z = __ldg(xyz + (int64_t)s_n * 3 + 2);
+    E.vbits = 0u;
+    int L = 1;
+    int emitted = 1;  // indices written so far; the last L of them are not applied yet
+    unsigned wbits = __float_as_uint(PLACEHOLDER_D2), vbits = __float_as_uint(PLACEHOLDER_D2);
+    int wi = INT_MAX, wslot = 0;
+    float tx = 0.f, ty = 0.f, tz = 0.f;  // coordinates of the warp's top point
+    bool dirty = true;  // the warp entry has to be (re)computed
+    unsigned long long n_rounds = 0;
+    int* out = idx + s_m;
+
+    for (int round = 0;; round++) {
+        // ---- apply the accepted samples: lane j tests sample j against the warp's box (exact pruning) ----
+        {
+            bool touch = lane < L;
+            if (prune && round > 0) {
+                const float ex = fmaxf(fmaxf(blo[0] - E.x, E.x - bhi[0]), 0.f);
+                const float ey = fmaxf(fmaxf(blo[1] - E.y, E.y - bhi[1]), 0.f);
+                const float ez = fmaxf(fmaxf(blo[2] - E.z, E.z - bhi[2]), 0.f);
+                const float b2 = __fmaf_rn(ez, ez, __fmaf_rn(ex, ex, __fmul_rn(ey, ey)));
+                // every d2_ref(point, sample) >= b2 * (1 - 1e-6); if even b2 * 0.99999 >= max tmp nothing changes
+                touch = touch && !(b2 * 0.99999f >= __uint_as_float(wbits));
+            }
+            unsigned tm = __ballot_sync(FULL, touch);
+            dirty = dirty || tm != 0u;
+            while (tm) {
+                const int j = __ffs(tm) - 1;
+                tm &= tm - 1;
+                const float sx = __shfl_sync(FULL, E.x, j), sy = __shfl_sync(FULL, E.y, j), sz = __shfl_sync(FULL, E.z, j);
+#pragma unroll
+                for (int p = 0; p < P; p++) pt[p] = fminf(d2_ref(px[p], py[p], pz[p], sx, sy, sz), pt[p]);
+            }
+        }
+        if (emitted >= total) break;  // uniform: `emitted` evolves identically in every thread of the cluster
+        n_rounds++;
+        if (dirty) {
+            dirty = false;
+            float m = 0.f;
+#pragma unroll
+            for (int p = 0; p < P; p++) m = fmaxf(m, pt[p]);
+            wbits = __reduce_max_sync(FULL, __float_as_uint(m));
+            int cand = INT_MAX, cp = 0;
+#pragma unroll
+            for (int p = 0; p < P; p++)
+                if (__float_as_uint(pt[p]) == wbits && pi[p] < cand) { cand = pi[p]; cp = p; }
+            wi = __reduce_min_sync(FULL, cand);
+            const unsigned own = __ballot_sync(FULL, cand == wi && wi != INT_MAX);
+            const int ol = own ? __ffs(own) - 1 : 0;
+            wslot = __shfl_sync(FULL, (warp * P + cp) * 32 + lane, ol);
+            // V_w: this warp's maximum if its own top point became a sample (dry run, nothing stored)
+            tx = s_xyz[wslot]; ty = s_xyz[T * P + wslot]; tz = s_xyz[2 * T * P + wslot];
+            float vm = 0.f;
+#pragma unroll
+            for (int p = 0; p < P; p++) vm = fmaxf(vm, fminf(d2_ref(px[p], py[p], pz[p], tx, ty, tz), pt[p]));
+            vbits = __reduce_max_sync(FULL, __float_as_uint(vm));
+        }
+        const int par = round & 1;
+        if (lane == 0) {   // parity buffers: a warp already in round r + 1 must not overwrite what round r still reads
+            FpsEntry e;
+            e.bits = wbits; e.idx = wi; e.x = tx; e.y = ty; e.z = tz; e.vbits = vbits; e.pad0 = e.pad1 = 0;
+            s_warp[par][warp] = e;
+        }
+        __syncthreads();  // warp entries of this round visible
+
+        const FpsEntry* src = s_warp[par];
+        if (C > 1) {
+            if (warp == 0) {
+                // this CTA's candidate: its best warp entry; V = max(V of that warp, runner-up warp maximum)
+                const FpsEntry e = s_warp[par][lane & (NG - 1)];
+                const unsigned eb = lane < NW ? e.bits : 0u;
+                const int ei = lane < NW ? e.idx : INT_MAX;
+                unsigned cbits; int ci;
+                warp_argmax(eb, ei, cbits, ci);
+                const unsigned whow = __ballot_sync(FULL, lane < NW && eb == cbits && ei == ci);
+                const int wl = whow ? __ffs(whow) - 1 : 0;
+                const unsigned second = __reduce_max_sync(FULL, (lane < NW && lane != wl) ? eb : 0u);
+                const unsigned vw = __shfl_sync(FULL, e.vbits, wl);
+                const unsigned cv = vw > second ? vw : second;
+                const float cx = __shfl_sync(FULL, e.x, wl), cy = __shfl_sync(FULL, e.y, wl), cz = __shfl_sync(FULL, e.z, wl);
+                if (lane < C) {
+                    const unsigned rs = par ? rslot1 : rslot0, rb = par ? rbar1 : rbar0;
+                    st_async_v4(rs, cbits, (unsigned)ci, __float_as_uint(cx), __float_as_uint(cy), rb);
+                    st_async_v4(rs + 16, __float_as_uint(cz), cv, 0u, 0u, rb);
+                }
+            }
+            mbar_wait(par ? bar1 : bar0, (unsigned)(round >> 1) & 1u);
+            src = s_msg[par];
+        }
+        // ---- every warp, redundantly: rank the 16 group slots by key, lay them out in order ----
+        const FpsEntry mine = src[lane & (NG - 1)];
+        const unsigned long long mykey = fps_key(mine.bits, mine.idx);
+        int rk = 0;
+#pragma unroll
+        for (int c = 0; c < NG; c++) {
+            const uint2 o = *reinterpret_cast<const uint2*>(&src[c]);  // {bits, idx}
+            rk += fps_key(o.x, (int)o.y) > mykey ? 1 : 0;
+        }
+        if (lane < NG) my_sorted[rk] = mine;   // equal keys only among empty slots (same content)
+        __syncwarp();
+        if (C > 1 && tid == 0) mbar_expect_tx(par ? bar1 : bar0, C * (int)sizeof(FpsEntry));  // re-arm for round + 2
+        // ---- longest accepted prefix: pair (a < b) needs "a_a leaves a_b untouched" and V_a < tmp[a_b] ----
+        bool ok = true;
+        if (pb < FPS_KMAX) {
+            const FpsEntry ea = my_sorted[pa], eb = my_sorted[pb];
+            const float d = d2_ref(eb.x, eb.y, eb.z, ea.x, ea.y, ea.z);   // exactly what the update computes for point b
+            ok = !(d < __uint_as_float(eb.bits)) && ea.vbits < eb.bits;
+        }
+        E = my_sorted[lane & (FPS_KMAX - 1)];
+        const unsigned bad = ~__ballot_sync(FULL, ok);
+        L = bad ? __shfl_sync(FULL, pb, __ffs(bad) - 1) : FPS_KMAX;  // pairs are pb-major: the first failing pair names L
+        if (L > total - emitted) L = total - emitted;
+        if (writer && lane < L) out[emitted + lane] = E.idx;
+        emitted += L;
+        __syncwarp();  // my_sorted is rewritten next round
+    }
+    if (stats && tid == 0 && rank == 0) {   // diagnostics: rounds and samples per scene (mean chain = samples / rounds)
+        atomicAdd(stats, n_rounds);
+        atomicAdd(stats + 1, (unsigned long long)(total - 1));
+    }
+    if (C > 1) cluster.sync();  // nobody leaves while a peer may still be writing into its shared memory
+}
+
 // Same algorithm with the points left in global memory (L2-resident for any realistic scene):
 // the fallback for scenes that do not fit the register-resident kernel.
 __global__ void __launch_bounds__(FPS_STREAM_THREADS, 1)
@@ -326,6 +589,16 @@ static int launch_cluster(const void* kernel, int b, int C, int threads, size_t 
 }
 
 template <int T>
+static int launch_chain(int P, int b, int C, cudaStream_t stream, void** args) {
+#define POB_FPS_CASE(PP) \
+    if (P <= PP) return launch_cluster((const void*)fps_chain_kernel<PP, T>, b, C, T, sizeof(float) * 3 * T * PP, stream, args)
+    POB_FPS_CASE(1); POB_FPS_CASE(2); POB_FPS_CASE(4); POB_FPS_CASE(6); POB_FPS_CASE(8); POB_FPS_CASE(12);
+    POB_FPS_CASE(16); POB_FPS_CASE(20); POB_FPS_CASE(24); POB_FPS_CASE(32);
+#undef POB_FPS_CASE
+    return POB_ERR_UNSUPPORTED;
+}
+
+template <int T>
 static int launch_resident(int P, int b, int C, cudaStream_t stream, void** args) {
 #define POB_FPS_CASE(PP) \
     if (P <= PP) return launch_cluster((const void*)fps_cluster_kernel<PP, T>, b, C, T, sizeof(float) * 3 * T * PP, stream, args)
@@ -338,6 +611,10 @@ static int launch_resident(int P, int b, int C, cudaStream_t stream, void** args
 }  // namespace pob
 
 using namespace pob;
+
+// optional diagnostics buffer (2 x u64 on the device: rounds, samples), set by pob_fps_set_stats
+static unsigned long long* g_fps_stats = nullptr;
+POB_API int pob_fps_set_stats(void* device_u64x2) { g_fps_stats = (unsigned long long*)device_u64x2; return 0; }
 
 // farthest_point_sampling_cuda_launcher(b, n, xyz, offset, new_offset, tmp, idx)
 // (sampling_cuda_kernel.h:13) + the optional kNN grid of the same (xyz, offset) + stream.
@@ -367,8 +644,16 @@ POB_API int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, 
     constexpr int PMAX = 32;    // registers: 5 per point + ~40
     int C = cluster_hint;
     if (C != 1 && C != 2 && C != 4 && C != 8 && C != 16) {
-        // ~200 ns of cluster exchange per iteration buys a 1/C share of the update work
-        C = n_max <= 4096 ? 1 : (n_max <= 16384 ? 4 : (n_max <= 40960 ? 8 : 16));
+        static const bool chain_mode = !(getenv("POINTOPS_B200_FPS") && strcmp(getenv("POINTOPS_B200_FPS"), "single") == 0);
+        if (chain_mode) {
+            // a round costs ~1.1-1.5 us whatever C is, and accepts more samples the more groups compete
+            // (measured mean chain 2.2 / 2.9 / 4.0-4.5 at C = 4 / 8 / 16): 16 CTAs unless the scene is tiny
+            // or there are so many scenes that 16-CTA clusters could not all be resident (8 GPCs)
+            C = n_max <= 2048 ? 1 : (b <= 8 ? 16 : (b <= 16 ? 8 : 4));
+        } else {
+            // ~200 ns of cluster exchange per iteration buys a 1/C share of the update work
+            C = n_max <= 4096 ? 1 : (n_max <= 16384 ? 4 : (n_max <= 40960 ? 8 : 16));
+        }
     }
     while (C < 16 && ceil_div(n_max, (int64_t)C * T) > PMAX) C *= 2;
     const int64_t P = ceil_div(n_max, (int64_t)C * T);
@@ -376,6 +661,14 @@ POB_API int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, 
         if (!tmp) return POB_ERR_BAD_ARG;
         void* args[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&tmp, (void*)&idx};
         return launch_cluster((const void*)fps_stream_kernel, b, 16, FPS_STREAM_THREADS, 0, stream, args);
+    }
+    // POINTOPS_B200_FPS=single selects the one-sample-per-exchange kernel (A/B and fallback)
+    static const bool use_chain = !(getenv("POINTOPS_B200_FPS") && strcmp(getenv("POINTOPS_B200_FPS"), "single") == 0);
+    if (use_chain) {
+        unsigned long long* stats = g_fps_stats;
+        void* cargs[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&scenes, (void*)&cell_start,
+                         (void*)&sorted, (void*)&idx, (void*)&stats};
+        return launch_chain<T>((int)P, b, C, stream, cargs);
     }
     void* args[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&scenes, (void*)&cell_start,
                     (void*)&sorted, (void*)&idx};

@@ -172,7 +172,7 @@ _knn_results = _LRU(_KNN_CACHE_SIZE)
 
 
 def _stream_id(dev) -> int:
-    return int(torch.cuda.current_stream(dev).cuda_stream)
+    return _lib.raw_stream(dev)
 
 
 def get_grid(xyz: torch.Tensor, offset: torch.Tensor) -> NeighbourGrid:

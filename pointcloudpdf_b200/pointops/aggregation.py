@@ -25,7 +25,7 @@ class Aggregation(Function):
         if c % w_c:
             raise ValueError("aggregation: weight channels must divide feature channels")
         output = torch.empty((n, c), dtype=torch.float32, device=input.device)
-        with torch.cuda.device(input.device):
+        with _lib.device_guard(input.device):
             _lib.run("pob_aggregation_forward", n, nsample, c, w_c, _lib.ptr(input), _lib.ptr(position),
                      _lib.ptr(weight), _lib.ptr(idx), _lib.ptr(output), _lib.current_stream(input.device),
                      alg_bytes=4 * (input.shape[0] * c + n * nsample * c + n * nsample * w_c + n * nsample + n * c))
@@ -42,7 +42,7 @@ class Aggregation(Function):
         grad_input = torch.zeros_like(input)
         grad_position = torch.empty_like(position)
         grad_weight = torch.empty_like(weight)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             fwd_in = input.shape[0] * c + n * nsample * c + n * nsample * w_c + n * nsample
             _lib.run("pob_aggregation_backward", n, nsample, c, w_c, _lib.ptr(input), _lib.ptr(position),
                      _lib.ptr(weight), _lib.ptr(idx), _lib.ptr(grad_output), _lib.ptr(grad_input),

@@ -60,7 +60,7 @@ def pt_layer_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, xyz: tor
         raise ValueError(f"pt_layer_forward: unsupported C={c} / nsample={ns}")
     out = torch.empty((n, c), dtype=torch.float32, device=q.device)
     wc = c // 8
-    with torch.cuda.device(q.device):
+    with _lib.device_guard(q.device):
         _lib.run("pob_pt_layer_forward", n, ns, c, wc, _lib.ptr(q), q.stride(0), _lib.ptr(k), k.stride(0),
                  _lib.ptr(v), v.stride(0), _lib.ptr(xyz), _lib.ptr(idx), _lib.ptr(params), int(bool(out_affine)),
                  _lib.ptr(out), c, _lib.current_stream(q.device),
@@ -76,7 +76,7 @@ def affine_act(x: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[t
     C.require(x, "x", torch.float32, 2)
     rows, c = x.shape
     out = x if inplace else torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _lib.device_guard(x.device):
         _lib.run("pob_affine_act", rows, c, _lib.ptr(x), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(residual),
                  int(bool(relu)), _lib.ptr(out), _lib.current_stream(x.device),
                  alg_bytes=4 * rows * c * (2 + (residual is not None)))
@@ -96,7 +96,7 @@ def interpolation_add(feat: torch.Tensor, idx: torch.Tensor, weight: torch.Tenso
         if base.shape != (n, c):
             raise ValueError("interpolation_add: base must be (n, c)")
     out = base if (inplace and base is not None) else torch.empty((n, c), dtype=torch.float32, device=feat.device)
-    with torch.cuda.device(feat.device):
+    with _lib.device_guard(feat.device):
         _lib.run("pob_interpolation_add_forward", n, c, k, _lib.ptr(feat), _lib.ptr(idx), _lib.ptr(weight),
                  _lib.ptr(base), _lib.ptr(out), _lib.current_stream(feat.device),
                  alg_bytes=4 * (feat.shape[0] * c + 2 * n * k + n * c * (1 + (base is not None))))
@@ -122,7 +122,7 @@ def transition_down_pool(z: torch.Tensor, xyz: torch.Tensor, new_xyz: torch.Tens
     if new_xyz.shape[0] != m or xyz.shape[0] != z.shape[0] or wxyz.shape[0] != c:
         raise ValueError("transition_down_pool: inconsistent shapes")
     out = torch.empty((m, c), dtype=torch.float32, device=z.device)
-    with torch.cuda.device(z.device):
+    with _lib.device_guard(z.device):
         _lib.run("pob_transition_down_pool", m, ns, c, _lib.ptr(z), _lib.ptr(xyz), _lib.ptr(new_xyz), _lib.ptr(idx),
                  _lib.ptr(wxyz), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(out), _lib.current_stream(z.device),
                  alg_bytes=4 * (z.shape[0] * c + 3 * z.shape[0] + 3 * m + m * ns + m * c))

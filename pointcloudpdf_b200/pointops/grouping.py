@@ -22,7 +22,7 @@ class Grouping(Function):
         m, nsample = idx.shape
         n, c = input.shape
         output = torch.empty((m, nsample, c), dtype=torch.float32, device=input.device)
-        with torch.cuda.device(input.device):
+        with _lib.device_guard(input.device):
             _lib.run("pob_grouping_forward", m, nsample, c, _lib.ptr(input), _lib.ptr(idx), _lib.ptr(output),
                      _lib.current_stream(input.device), alg_bytes=4 * (n * c + m * nsample + m * nsample * c))
         ctx.n = n
@@ -35,7 +35,7 @@ class Grouping(Function):
         grad_output = grad_output.contiguous().float()
         m, nsample, c = grad_output.shape
         grad_input = torch.zeros((ctx.n, c), dtype=torch.float32, device=grad_output.device)
-        with torch.cuda.device(grad_output.device):
+        with _lib.device_guard(grad_output.device):
             _lib.run("pob_grouping_backward", m, nsample, c, _lib.ptr(grad_output), _lib.ptr(idx),
                      _lib.ptr(grad_input), _lib.current_stream(grad_output.device),
                      alg_bytes=4 * (ctx.n * c + m * nsample + m * nsample * c))
@@ -54,7 +54,7 @@ class _GroupXYZ(Function):
         n, c = feat.shape
         width = c + (3 if with_xyz else 0)
         out = torch.empty((m, nsample, width), dtype=torch.float32, device=feat.device)
-        with torch.cuda.device(feat.device):
+        with _lib.device_guard(feat.device):
             x3 = 3 if with_xyz else 0
             _lib.run("pob_group_xyz_forward", m, nsample, c, 1 if with_xyz else 0, _lib.ptr(feat),
                      _DTYPE_CODE[feat.dtype], _lib.ptr(xyz), _lib.ptr(new_xyz), _lib.ptr(idx), _lib.ptr(out),
@@ -71,7 +71,7 @@ class _GroupXYZ(Function):
         grad_out = grad_out.contiguous().float()
         m, nsample = idx.shape
         grad_feat = torch.zeros((n, c), dtype=torch.float32, device=grad_out.device)
-        with torch.cuda.device(grad_out.device):
+        with _lib.device_guard(grad_out.device):
             _lib.run("pob_group_xyz_backward", m, nsample, c, 1 if with_xyz else 0, _lib.ptr(grad_out),
                      _lib.ptr(idx), _lib.ptr(grad_feat), _lib.current_stream(grad_out.device),
                      alg_bytes=4 * (n * c + m * nsample + m * nsample * (c + (3 if with_xyz else 0))))
@@ -109,7 +109,7 @@ def grouping_split(idx, feat, xyz, new_xyz=None):
     C.require(new_xyz, "new_xyz", torch.float32, 2, 3)
     m, nsample = idx.shape
     rel = torch.empty((m, nsample, 3), dtype=torch.float32, device=xyz.device)
-    with torch.cuda.device(xyz.device):
+    with _lib.device_guard(xyz.device):
         _lib.run("pob_group_relxyz_forward", m, nsample, _lib.ptr(xyz), _lib.ptr(new_xyz), _lib.ptr(idx), _lib.ptr(rel),
                  _lib.current_stream(xyz.device), alg_bytes=4 * (3 * xyz.shape[0] + 3 * m + m * nsample + 3 * m * nsample))
     return rel, grouped

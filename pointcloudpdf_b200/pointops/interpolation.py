@@ -16,7 +16,7 @@ class _InterpolateRows(Function):
         n, k = idx.shape
         m, c = input.shape
         output = torch.empty((n, c), dtype=torch.float32, device=input.device)
-        with torch.cuda.device(input.device):
+        with _lib.device_guard(input.device):
             _lib.run("pob_interpolation_forward", n, c, k, _lib.ptr(input), _lib.ptr(idx), _lib.ptr(weight),
                      _lib.ptr(output), _lib.current_stream(input.device), alg_bytes=4 * (m * c + 2 * n * k + n * c))
         ctx.m = m
@@ -30,7 +30,7 @@ class _InterpolateRows(Function):
         n, c = grad_output.shape
         k = idx.shape[1]
         grad_input = torch.zeros((ctx.m, c), dtype=torch.float32, device=grad_output.device)
-        with torch.cuda.device(grad_output.device):
+        with _lib.device_guard(grad_output.device):
             _lib.run("pob_interpolation_backward", n, c, k, _lib.ptr(grad_output), _lib.ptr(idx), _lib.ptr(weight),
                      _lib.ptr(grad_input), _lib.current_stream(grad_output.device),
                      alg_bytes=4 * (ctx.m * c + 2 * n * k + n * c))
@@ -41,7 +41,7 @@ def _neighbours_and_weights(xyz, new_xyz, offset, new_offset, k):
     C.require(xyz, "xyz", torch.float32, 2, 3)
     C.require(new_xyz, "new_xyz", torch.float32, 2, 3)
     offset, new_offset = C.offset_i32(offset, "offset"), C.offset_i32(new_offset, "new_offset")
-    with torch.cuda.device(xyz.device):
+    with _lib.device_guard(xyz.device):
         idx, _, weight = C.cached_knn(int(k), xyz, offset, new_xyz, new_offset, want_weight=True)
     return idx, weight
 
@@ -76,7 +76,7 @@ class Interpolation(Function):
         idx = _wrap_placeholders(idx, input.shape[0])
         n, c, m = new_xyz.shape[0], input.shape[1], input.shape[0]
         output = torch.empty((n, c), dtype=torch.float32, device=input.device)
-        with torch.cuda.device(input.device):
+        with _lib.device_guard(input.device):
             _lib.run("pob_interpolation_forward", n, c, int(k), _lib.ptr(input), _lib.ptr(idx), _lib.ptr(weight),
                      _lib.ptr(output), _lib.current_stream(input.device), alg_bytes=4 * (m * c + 2 * n * int(k) + n * c))
         ctx.m, ctx.k = m, int(k)
@@ -89,7 +89,7 @@ class Interpolation(Function):
         grad_output = grad_output.contiguous().float()
         n, c = grad_output.shape
         grad_input = torch.zeros((ctx.m, c), dtype=torch.float32, device=grad_output.device)
-        with torch.cuda.device(grad_output.device):
+        with _lib.device_guard(grad_output.device):
             _lib.run("pob_interpolation_backward", n, c, ctx.k, _lib.ptr(grad_output), _lib.ptr(idx), _lib.ptr(weight),
                      _lib.ptr(grad_input), _lib.current_stream(grad_output.device),
                      alg_bytes=4 * (ctx.m * c + 2 * n * ctx.k + n * c))

@@ -4,6 +4,7 @@ from __future__ import annotations
 import torch
 from torch.autograd import Function
 
+from .. import _lib
 from . import _common as C
 
 
@@ -26,7 +27,7 @@ class KNNQuery(Function):
         C.same_device(("xyz", xyz), ("new_xyz", new_xyz), ("offset", offset), ("new_offset", new_offset))
         if offset.numel() != new_offset.numel():
             raise ValueError("offset and new_offset must describe the same number of scenes")
-        with torch.cuda.device(xyz.device):
+        with _lib.device_guard(xyz.device):
             idx, dist, _ = C.cached_knn(nsample, xyz, offset, new_xyz, new_offset)
         ctx.mark_non_differentiable(idx, dist)
         return idx, dist

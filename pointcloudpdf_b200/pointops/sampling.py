@@ -12,6 +12,30 @@ from . import _common as C
 USE_GRID = os.environ.get("POINTOPS_B200_FPS_GRID", "1") != "0"
 
 
+def fps_launch(xyz, offset, new_offset, offset_host, new_offset_host):
+    """The launch itself, for callers that already validated their tensors and know the host copies
+    of both offset vectors (the PTv1 mirror's geometry pass): no checks, no autograd node."""
+    sizes = C.scene_sizes(offset_host)
+    m = new_offset_host[-1]
+    n_max = max(sizes) if sizes else 0
+    idx = torch.empty((m,), dtype=torch.int32, device=xyz.device)
+    if m == 0:
+        return idx
+    tmp = None
+    if n_max > 131072:  # beyond the register-resident capacity the kernel streams through tmp
+        tmp = torch.empty((xyz.shape[0],), dtype=torch.float32, device=xyz.device)
+    with _lib.device_guard(xyz.device):
+        flops = sum(10 * max(mb - 1, 0) * nb for nb, mb in zip(sizes, C.scene_sizes(new_offset_host)))
+        # the search grid of this cloud (built once, reused by the kNN queries that follow in
+        # TransitionDown) gives the kernel cell-ordered points for exact pruning
+        grid = C.get_grid(xyz, offset) if (USE_GRID and n_max > 2048) else None
+        _lib.run("pob_farthest_point_sampling", offset.numel(), n_max, _lib.ptr(xyz), _lib.ptr(offset), _lib.ptr(new_offset),
+                 _lib.ptr(tmp), _lib.ptr(idx), 0, _lib.ptr(grid.workspace if grid else None),
+                 xyz.shape[0], grid.cell_pts if grid else 0.0, _lib.current_stream(xyz.device),
+                 alg_bytes=12 * xyz.shape[0] + 4 * m, alg_flops=flops)
+    return idx
+
+
 class FarthestPointSampling(Function):
     @staticmethod
     def forward(ctx, xyz, offset, new_offset):
@@ -22,30 +46,11 @@ class FarthestPointSampling(Function):
         C.require(xyz, "xyz", torch.float32, 2, 3)
         offset, new_offset = C.offset_i32(offset, "offset"), C.offset_i32(new_offset, "new_offset")
         C.same_device(("xyz", xyz), ("offset", offset), ("new_offset", new_offset))
-        b = offset.numel()
-        if new_offset.numel() != b:
+        if new_offset.numel() != offset.numel():
             raise ValueError("offset and new_offset must describe the same number of scenes")
-        # the two host numbers the launch needs; registered by callers that know them, else one
+        # the host numbers the launch needs; registered by callers that know them, else one
         # .tolist() per offset tensor (the reference syncs once per scene, sampling.py:15-18)
-        sizes = C.scene_sizes(C.host_offset(offset))
-        m = C.host_offset(new_offset)[-1]
-        n_max = max(sizes) if sizes else 0
-        idx = torch.empty((m,), dtype=torch.int32, device=xyz.device)
-        if m == 0:
-            return idx
-        tmp = None
-        if n_max > 131072:  # beyond the register-resident capacity the kernel streams through tmp
-            tmp = torch.empty((xyz.shape[0],), dtype=torch.float32, device=xyz.device)
-        with torch.cuda.device(xyz.device):
-            noff = C.host_offset(new_offset)
-            flops = sum(10 * max(mb - 1, 0) * nb for nb, mb in zip(sizes, C.scene_sizes(noff)))
-            # the search grid of this cloud (built once, reused by the kNN queries that follow in
-            # TransitionDown) gives the kernel cell-ordered points for exact pruning
-            grid = C.get_grid(xyz, offset) if (USE_GRID and n_max > 2048) else None
-            _lib.run("pob_farthest_point_sampling", b, n_max, _lib.ptr(xyz), _lib.ptr(offset), _lib.ptr(new_offset),
-                     _lib.ptr(tmp), _lib.ptr(idx), 0, _lib.ptr(grid.workspace if grid else None),
-                     xyz.shape[0], grid.cell_pts if grid else 0.0, _lib.current_stream(xyz.device),
-                     alg_bytes=12 * xyz.shape[0] + 4 * m, alg_flops=flops)
+        idx = fps_launch(xyz, offset, new_offset, C.host_offset(offset), C.host_offset(new_offset))
         ctx.mark_non_differentiable(idx)
         return idx
 

@@ -20,7 +20,7 @@ class Subtraction(Function):
         n, c = input1.shape
         nsample = idx.shape[-1]
         output = torch.empty((n, nsample, c), dtype=torch.float32, device=input1.device)
-        with torch.cuda.device(input1.device):
+        with _lib.device_guard(input1.device):
             _lib.run("pob_subtraction_forward", n, nsample, c, _lib.ptr(input1), _lib.ptr(input2), _lib.ptr(idx),
                      _lib.ptr(output), _lib.current_stream(input1.device),
                      alg_bytes=4 * (2 * n * c + n * nsample + n * nsample * c))
@@ -36,7 +36,7 @@ class Subtraction(Function):
         dev = grad_output.device
         grad_input1 = torch.empty((n, c), dtype=torch.float32, device=dev)
         grad_input2 = torch.zeros((ctx.n2, c), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.run("pob_subtraction_backward", n, nsample, c, _lib.ptr(idx), _lib.ptr(grad_output),
                      _lib.ptr(grad_input1), _lib.ptr(grad_input2), _lib.current_stream(dev),
                      alg_bytes=4 * (n * nsample * c + n * nsample + 2 * n * c))

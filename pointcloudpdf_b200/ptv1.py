@@ -29,8 +29,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import pointops
+from . import _lib, pointops
 from .pointops import _common as C
+from .pointops.sampling import fps_launch
 from .pointops import fused as FZ
 
 
@@ -121,7 +122,7 @@ class Level:
 
 def _wait(ev):
     if ev is not None:
-        torch.cuda.current_stream().wait_event(ev)
+        _lib.current_stream_obj().wait_event(ev)
 
 
 class Cloud:
@@ -436,7 +437,9 @@ class PointTransformerSeg(_Freezable, nn.Module):
         with weights -- issued on `stream` so that it overlaps the feature path (FPS is a serial,
         16-SM kernel; the linears run on the other SMs meanwhile).  Each item carries the event
         the feature path waits on.  Results are bit-identical to computing them inline."""
-        main = torch.cuda.current_stream()
+        C.require(p0, "coord", torch.float32, 2, 3)   # validated once here; the launches below skip the per-op checks
+        o0 = C.offset_i32(o0, "offset")
+        main = _lib.current_stream_obj(p0.device)
         stream = stream if stream is not None else main
         strides = [m[0].stride for m in (self.enc1, self.enc2, self.enc3, self.enc4, self.enc5)]
         nsamples = [m[0].nsample for m in (self.enc1, self.enc2, self.enc3, self.enc4, self.enc5)]
@@ -448,7 +451,7 @@ class PointTransformerSeg(_Freezable, nn.Module):
             lvl = Level(p0, o0, offset_host)
             for s in range(5):
                 levels.append(lvl)
-                lvl.knn[nsamples[s]] = pointops.knn_query(nsamples[s], lvl.p, lvl.o)[0]
+                lvl.knn[nsamples[s]] = C.cached_knn(nsamples[s], lvl.p, lvl.o, lvl.p, lvl.o)[0]
                 lvl.knn_ev = torch.cuda.Event()
                 lvl.knn_ev.record(stream)
                 keep.append(lvl.knn[nsamples[s]])
@@ -457,11 +460,12 @@ class PointTransformerSeg(_Freezable, nn.Module):
                 n_o_host = strided_offsets(lvl.o_host, strides[s + 1])
                 n_o = torch.tensor(n_o_host, dtype=torch.int32).to(lvl.p.device, non_blocking=True)
                 C.register_host_offset(n_o, n_o_host)
-                sel = pointops.farthest_point_sampling(lvl.p, lvl.o, n_o)
-                n_p = lvl.p[sel.long(), :]
-                cross = pointops.knn_query(nsamples[s + 1], lvl.p, lvl.o, n_p, n_o)[0]
+                sel = fps_launch(lvl.p, lvl.o, n_o, lvl.o_host, n_o_host)
+                n_p = lvl.p.index_select(0, sel)
+                cross = C.cached_knn(nsamples[s + 1], lvl.p, lvl.o, n_p, n_o)[0]
                 up_idx, _, up_w = C.cached_knn(3, n_p, n_o, lvl.p, lvl.o, want_weight=True)
-                up_idx = torch.where(up_idx < 0, up_idx + n_p.shape[0], up_idx)  # quirk C6, as pointops.interpolation
+                if min(C.scene_sizes(n_o_host)) < 3:  # quirk C6, as pointops.interpolation: -1 indexes feat[-1]
+                    up_idx = torch.where(up_idx < 0, up_idx + n_p.shape[0], up_idx)
                 lvl.down = dict(n_p=n_p, n_o=n_o, n_o_host=n_o_host, cross=cross, up_idx=up_idx, up_w=up_w)
                 lvl.down_ev = torch.cuda.Event()
                 lvl.down_ev.record(stream)

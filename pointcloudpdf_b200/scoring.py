@@ -57,7 +57,7 @@ def fused_scores(logits: torch.Tensor, conf: Optional[torch.Tensor] = None, offs
         ws_bytes = lib.pob_score_workspace_bytes(b)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         out["scene"] = torch.empty((b, 8), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         n_out = sum(k != "scene" for k in out)
         _lib.run("pob_score_fused", n, K, b, _lib.ptr(logits), _lib.ptr(conf), _lib.ptr(off32), float(beta),
                  _lib.ptr(out.get("msp_score")), _lib.ptr(out.get("ml_score")), _lib.ptr(out.get("pdf_score")),
