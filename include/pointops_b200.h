@@ -167,6 +167,11 @@ int pob_group_relxyz_forward(int64_t m, int nsample, const float* xyz, const flo
  * fine); out (n, c) with row stride ldo.  Supported: c in {32,64,128,256,512}, w_c = c/8, nsample in {8,16};
  * anything else returns POB_ERR_UNSUPPORTED (callers then run the unfused operator sequence).      */
 int64_t pob_pt_layer_param_floats(int c, int w_c);
+/* Tuning / test hook.  0 (default): the CTA-tiled kernel (needs 16-byte aligned rows, else falls back);
+ * 1, 4, 8, 16: the warp-per-point kernel with that many warps sharing one point (clamped to what the
+ * shape instantiates); -1: warp-per-point with the split chosen from n.  Only the f32 summation order
+ * depends on it.                                                                                   */
+int pob_pt_layer_set_split(int warps_per_point);
 int pob_pt_layer_forward(int64_t n, int nsample, int c, int w_c, const float* q, int64_t ldq, const float* k,
                          int64_t ldk, const float* v, int64_t ldv, const float* xyz, const int* idx,
                          const float* params, int out_affine, float* out, int64_t ldo, cudaStream_t stream);

@@ -41,8 +41,11 @@ def layer_reference(layer, bn2, x_q, x_k, x_v, xyz, idx):
 
 @pytest.mark.parametrize("c,ns", [(32, 8), (64, 16), (128, 16), (256, 16), (512, 16), (32, 16), (128, 8)])
 @pytest.mark.parametrize("tail", [True, False])
-def test_pt_layer_forward_matches_torch(cuda, c, ns, tail):
-    from pointcloudpdf_b200 import ptv1, synthetic as S
+@pytest.mark.parametrize("split", [0, -1, 1, 4, 16])
+def test_pt_layer_forward_matches_torch(cuda, c, ns, tail, split):
+    """split: 0 = the CTA-tiled kernel (default), -1 / 1 / 4 / 16 = warp-per-point variants: every kernel
+    (one warp per point, 4 warps, one warp per neighbour) must agree with the torch restatement."""
+    from pointcloudpdf_b200 import _lib, ptv1, synthetic as S
     from pointcloudpdf_b200.pointops import fused as FZ
     import pointops
     gen = torch.Generator().manual_seed(c * 100 + ns)
@@ -62,7 +65,11 @@ def test_pt_layer_forward_matches_torch(cuda, c, ns, tail):
     with torch.no_grad():
         ref = layer_reference(block.transformer, block.bn2 if tail else None, q, k, v, xyz, idx)
         f = block.frozen()
-        out = FZ.pt_layer_forward(q, k, v, xyz, idx, f["params"], out_affine=tail)
+        _lib.load().pob_pt_layer_set_split(split)
+        try:
+            out = FZ.pt_layer_forward(q, k, v, xyz, idx, f["params"], out_affine=tail)
+        finally:
+            _lib.load().pob_pt_layer_set_split(0)
     err = (out - ref).abs().max().item()
     assert err <= 1e-5 * max(ref.abs().max().item(), 1.0), err
 
