@@ -196,5 +196,14 @@ def run(name: str, *args, alg_bytes: int = 0, alg_flops: int = 0) -> None:
     check(rc, name)
 
 
+_REPLAYED = 0  # kernels of this library launched through CUDA-graph replays (counted at capture time)
+
+
+def add_replayed_launches(n: int) -> None:
+    global _REPLAYED
+    _REPLAYED += int(n)
+
+
 def launch_count() -> int:
-    return int(load().pob_kernel_launch_count())
+    """Kernels of this library launched so far: direct launches (counted in C) + graph replays."""
+    return int(load().pob_kernel_launch_count()) + _REPLAYED

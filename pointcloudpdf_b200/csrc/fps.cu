@@ -351,10 +351,13 @@ fps_chain_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
     }
     const bool prune = in_cells && __all_sync(FULL, box_ok);
 
-    // zero the group slots (a zero entry ranks below every real candidate and is never accepted)
+    // empty group slots: value 0 and index -1, the smallest key there is -- below every real candidate even
+    // when all remaining min-distances are 0 (duplicate points: the real keys are then (0, ~idx) with
+    // idx >= 0), and never accepted into a chain (acceptance needs V < 0 as unsigned)
     for (int i = tid; i < 2 * NG * (int)(sizeof(FpsEntry) / 16); i += T) {
-        reinterpret_cast<float4*>(s_warp)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        reinterpret_cast<float4*>(s_msg)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 z = (i & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(0.f, __int_as_float(-1), 0.f, 0.f);
+        reinterpret_cast<float4*>(s_warp)[i] = z;
+        reinterpret_cast<float4*>(s_msg)[i] = z;
     }
     const bool writer = rank == 0 && warp == 0;
     const unsigned bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]);

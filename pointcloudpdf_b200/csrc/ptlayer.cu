@@ -340,12 +340,14 @@ static int launch_pt_layer(int64_t n, const float* q, int64_t ldq, const float* 
 // so k and v rows are gathered once each, every weight is read from shared memory once per tile, and
 // the per-pair work is the C * C/8 FMAs of the projection plus ~20 instructions.
 // FP32 on CUDA cores throughout (north_star: f32 means f32; the projection is 0.16 GFLOP per call).
-constexpr int PTT_THREADS = 256;
 
 template <int C, int NS>
 struct PtTile {
     static constexpr int WC = C / 8;
-    static constexpr int ROWS = C <= 64 ? 256 : (C == 128 ? 128 : (C == 256 ? 64 : 32));
+    // 2048 projection outputs per 256 threads (2 rows x 4 outputs each); the two deepest stages have so few
+    // points (1 250, 312) that half-size CTAs are used to get more independent tiles per SM
+    static constexpr int PTT_THREADS = C >= 256 ? 128 : 256;
+    static constexpr int ROWS = C <= 64 ? 256 : (C == 128 ? 128 : (C == 256 ? 32 : 16));
     static constexpr int P = ROWS / NS;                 // points per tile
     static constexpr int CK = C <= 64 ? 32 : (C == 128 ? 64 : 128);   // channels per chunk (sizes the t tile: ~35 KB)
     static constexpr int NCH = C / CK, CK4 = CK / 4, C4 = C / 4;
@@ -379,12 +381,13 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc)
 }
 
 template <int C, int NS>
-__global__ void __launch_bounds__(PTT_THREADS, 3)
+__global__ void __launch_bounds__((PtTile<C, NS>::PTT_THREADS), 3)
 pt_layer_tile_kernel(int64_t n, const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
                      const float* __restrict__ v, int64_t ldv, const float* __restrict__ xyz,
                      const int* __restrict__ idx, const float* __restrict__ params, int out_affine,
                      float* __restrict__ out, int64_t ldo) {
     using T = PtTile<C, NS>;
+    constexpr int PTT_THREADS = T::PTT_THREADS;
     constexpr int WC = T::WC, ROWS = T::ROWS, P = T::P, CK = T::CK, CK4 = T::CK4, C4 = T::C4, TS = T::TS;
     constexpr int OGS = T::OGS, RGS = T::RGS, RT = T::RT, RSTEP = T::RSTEP, IPT = T::IPT;
     extern __shared__ __align__(16) float smem[];
@@ -588,7 +591,7 @@ static int launch_pt_layer_tile(int64_t n, const float* q, int64_t ldq, const fl
     auto kern = pt_layer_tile_kernel<C, NS>;
     if (smem > 48 * 1024) POB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = ceil_div(n, T::P);
-    kern<<<(unsigned)grid, PTT_THREADS, smem, stream>>>(n, q, ldq, k, ldk, v, ldv, xyz, idx, params, out_affine, out, ldo);
+    kern<<<(unsigned)grid, T::PTT_THREADS, smem, stream>>>(n, q, ldq, k, ldk, v, ldv, xyz, idx, params, out_affine, out, ldo);
     pob_count_launches(1);
     POB_RETURN_LAST_ERROR();
 }

@@ -102,6 +102,24 @@ def host_offset(t: torch.Tensor) -> List[int]:
     return vals
 
 
+_CONST_OFFSETS = {}
+
+
+def const_offset(values: Sequence[int], device) -> torch.Tensor:
+    """Device int32 tensor holding `values`, memoised BY VALUE (a constant, so sharing it is safe and it
+    survives clear_caches): callers that derive offsets on the host (the PTv1 mirror's stage sizes) pay
+    the host->device copy once per distinct value, and the call is legal inside a CUDA-graph capture
+    once the value has been seen.  Treat the result as read-only."""
+    vals = tuple(int(v) for v in values)
+    k = (vals, device.index if device.index is not None else torch.cuda.current_device())
+    t = _CONST_OFFSETS.get(k)
+    if t is None:
+        if len(_CONST_OFFSETS) > 4096:
+            _CONST_OFFSETS.clear()
+        t = _CONST_OFFSETS[k] = torch.tensor(vals, dtype=torch.int32).to(device)
+    return t
+
+
 def scene_sizes(vals: Sequence[int]) -> List[int]:
     return [e - s for s, e in zip([0] + list(vals[:-1]), vals)]
 

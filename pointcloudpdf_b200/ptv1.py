@@ -251,7 +251,7 @@ class TransitionDown(_Freezable, nn.Module):
             nxt = lvl.coarser
         else:
             n_o_host = strided_offsets(cloud.o_host, self.stride)
-            n_o = torch.tensor(n_o_host, dtype=torch.int32).to(p.device, non_blocking=True)
+            n_o = C.const_offset(n_o_host, p.device)
             C.register_host_offset(n_o, n_o_host)
             C.register_host_offset(o, cloud.o_host)
             idx = pointops.farthest_point_sampling(p, o, n_o)          # (m)
@@ -309,7 +309,7 @@ class TransitionUp(_Freezable, nn.Module):
                 mean = x.sum(0, keepdim=True) / sizes[0]
                 tiled = self.linear2(mean).expand(x.shape[0], -1)
             else:
-                counts = torch.tensor(sizes, dtype=torch.int64).to(x.device, non_blocking=True)
+                counts = C.const_offset(sizes, x.device).long()
                 batch = torch.repeat_interleave(torch.arange(b, device=x.device), counts, output_size=x.shape[0])
                 sums = torch.zeros((b, x.shape[1]), dtype=x.dtype, device=x.device).index_add_(0, batch, x)
                 tiled = self.linear2(sums / counts.to(x.dtype).unsqueeze(1))[batch]
@@ -458,7 +458,7 @@ class PointTransformerSeg(_Freezable, nn.Module):
                 if s == 4:
                     break
                 n_o_host = strided_offsets(lvl.o_host, strides[s + 1])
-                n_o = torch.tensor(n_o_host, dtype=torch.int32).to(lvl.p.device, non_blocking=True)
+                n_o = C.const_offset(n_o_host, lvl.p.device)
                 C.register_host_offset(n_o, n_o_host)
                 sel = fps_launch(lvl.p, lvl.o, n_o, lvl.o_host, n_o_host)
                 n_p = lvl.p.index_select(0, sel)
@@ -472,7 +472,7 @@ class PointTransformerSeg(_Freezable, nn.Module):
                 keep += [n_p, n_o, cross, up_idx, up_w]
                 lvl.coarser = Level(n_p, n_o, n_o_host)
                 lvl = lvl.coarser
-        if stream is not main:
+        if stream is not main and not torch.cuda.is_current_stream_capturing():
             for t in keep:
                 t.record_stream(main)  # consumed by kernels on the main stream
         return levels
@@ -565,6 +565,56 @@ class PTRecognizer(_Freezable, nn.Module):
         return dict(hid=(W.t(), b), out=(Wo.t(), bo))
 
 
+class _RoomGraph:
+    """One stream slot of OpenSegPTv1.infer_stream for one size signature: static input buffers, the
+    captured forward (geometry branch on a forked stream + feature branch, joined), static outputs.
+    Replaying it costs the host a few calls instead of ~220 kernel launches plus their python."""
+
+    def __init__(self, model: "OpenSegPTv1", offset_host, in_channels: int, device):
+        self.offset_host = [int(v) for v in offset_host]
+        n = self.offset_host[-1]
+        self.stream = torch.cuda.Stream(device=device)
+        self.coord = torch.empty((n, 3), dtype=torch.float32, device=device)
+        self.feat = torch.empty((n, in_channels), dtype=torch.float32, device=device)
+        self.offset = C.const_offset(self.offset_host, device)
+        self.coord.zero_()
+        self.feat.zero_()
+        d = dict(coord=self.coord, feat=self.feat, offset=self.offset)
+        torch.cuda.synchronize(device)
+        with torch.cuda.stream(self.stream):
+            # eager dry run: folds the BatchNorms, creates the constant offset tensors, the geometry
+            # stream, cuBLAS handles / workspaces -- nothing lazy may be left for the capture
+            model.forward(d, self.offset_host)
+        torch.cuda.synchronize(device)
+        pointops.clear_caches()      # the capture must launch every kernel itself
+        self.graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        # thread_local: other threads of the process (NCCL watchdog, data loaders) may keep calling CUDA
+        with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode="thread_local"):
+            out = model.forward(d, self.offset_host)
+        self.launches = _lib.launch_count() - before   # kernels of ours inside one replay
+        pointops.clear_caches()      # entries keyed on the graph's private buffers are of no use to anyone
+        self.score, self.pred = out["score"], out["pred"]
+        model.backbone.taps = None   # the taps of the capture pass point into the graph's private pool
+
+    def run(self, coord: torch.Tensor, feat: torch.Tensor):
+        """Queue one room on this slot's stream; returns (event, score, pred) with score / pred in
+        pinned host memory, valid once the event has completed."""
+        n = self.coord.shape[0]
+        score = torch.empty((n,), dtype=torch.float32, pin_memory=True)
+        pred = torch.empty((n,), dtype=torch.int32, pin_memory=True)
+        with torch.cuda.stream(self.stream):
+            self.coord.copy_(coord, non_blocking=True)
+            self.feat.copy_(feat, non_blocking=True)
+            self.graph.replay()
+            _lib.add_replayed_launches(self.launches)
+            score.copy_(self.score, non_blocking=True)
+            pred.copy_(self.pred, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return done, score, pred
+
+
 class OpenSegPTv1(nn.Module):
     """What an ``openseg-pt-v1-0-{msp,ml,pointpdf}`` evaluation step computes per batch
     (hooks/evaluator.py:39-72): backbone logits, then the recognizer's open-set score.
@@ -577,6 +627,7 @@ class OpenSegPTv1(nn.Module):
         self.method = method
         self.recognizer = PTRecognizer() if method == "pdf" else None
         self._streams = []
+        self._graphs = {}   # (scene sizes, feature width) -> [_RoomGraph per stream slot]
 
     def forward(self, data_dict, offset_host=None, geometry=None):
         from .scoring import fused_scores
@@ -602,20 +653,60 @@ class OpenSegPTv1(nn.Module):
         return out["score"].cpu(), out["pred"].cpu()
 
     @torch.no_grad()
-    def infer_stream(self, rooms, depth: int = 2, device=None):
+    def infer_stream(self, rooms, depth: int = 2, device=None, graphs="auto"):
         """Serve a sequence of rooms ``(coord, feat, offset)`` (host tensors, pinned recommended),
         yielding ``(score, pred)`` host tensors per room, in order.
 
-        Same arithmetic as calling ``infer`` room by room; what changes is the schedule: the
-        host->device copy and the coordinate-only work (FPS, kNN) of the next ``depth`` rooms run
-        ahead on their own streams while the feature path of the current room runs on the main
-        stream, and the host only blocks on a room's result after the next room has been queued.
-        FPS is a serial 16-SM kernel, so this keeps the other 132 SMs busy."""
+        Same arithmetic as calling ``infer`` room by room; what changes is the schedule: up to
+        ``depth`` rooms are in flight, so the serial FPS chains (16 SMs each) of the next rooms run
+        under the feature path of the current one.
+
+        graphs: "auto" (default) replays a CUDA graph of the whole room -- coordinate branch and
+        feature branch with their fork/join, ~220 launches -- when every room of the call has the
+        same scene sizes (a graph is captured per size signature and stream slot, once); rooms of
+        differing sizes are launched eagerly.  False forces eager launches, True requires graphs."""
         dev = device if device is not None else next(self.parameters()).device
+        rooms = list(rooms)
+        if not rooms:
+            return
+        use_graphs = False
+        if graphs and not self.training:
+            sigs = {(tuple(C.host_offset(r[2]) if r[2].is_cuda else r[2].tolist()), int(r[1].shape[1])) for r in rooms}
+            use_graphs = len(sigs) == 1 and (graphs is True or len(rooms) >= 2 or next(iter(sigs)) in self._graphs)
+            if graphs is True and len(sigs) != 1:
+                raise ValueError("infer_stream(graphs=True) needs rooms of identical scene sizes")
+        if use_graphs:
+            yield from self._infer_stream_graphs(rooms, next(iter(sigs)), depth, dev)
+        else:
+            yield from self._infer_stream_eager(rooms, depth, dev)
+
+    def _infer_stream_graphs(self, rooms, sig, depth, dev):
+        slots = self._graphs.setdefault(sig, [])
+        while len(slots) < min(depth, len(rooms)):
+            slots.append(_RoomGraph(self, sig[0], sig[1], dev))
+        n_slots = len(slots)
+        inflight = {}
+
+        def launch(i):
+            coord, feat, _ = rooms[i]
+            inflight[i] = slots[i % n_slots].run(coord, feat)
+
+        for i in range(min(n_slots, len(rooms))):
+            launch(i)
+        for i in range(len(rooms)):
+            done, score, pred = inflight.pop(i)
+            done.synchronize()
+            if i + n_slots < len(rooms):
+                launch(i + n_slots)   # the slot's previous results are already in their own host buffers
+            yield score, pred
+
+    def _infer_stream_eager(self, rooms, depth, dev):
+        """One room after the other on the main stream; the host->device copy and the coordinate-only
+        work (FPS, kNN) of the next ``depth`` rooms run ahead on their own streams, and the host only
+        blocks on a room's result after the next room has been queued."""
         if len(self._streams) < depth:
             self._streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
         main = torch.cuda.current_stream(dev)
-        rooms = list(rooms)
         prepared = {}
 
         def prepare(i):

@@ -1,4 +1,5 @@
-import json, sys
+import json, sys, signal
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 d = json.load(open(sys.argv[1]))
 print({k: d[k] for k in ("value","ms_per_step","gpu_launches_per_step","clocks")})
 print("e2e", d["e2e"]); print("cpu", d.get("cpu_baseline"))

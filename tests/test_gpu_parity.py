@@ -171,6 +171,25 @@ def test_fps_ties_lowest_index(cuda, oracle):
     assert torch.equal(out.cpu(), ref)
 
 
+@pytest.mark.parametrize("sizes,distinct", [([5000, 1200], 1), ([3000], 100), ([9000, 2600], 700)])
+def test_fps_duplicate_points_all_distances_zero(cuda, oracle, sizes, distinct):
+    """More samples requested than there are distinct positions: once every position is taken all
+    remaining min-distances are 0 and the tie rule (lowest index) decides every further sample --
+    including the fully degenerate cloud (every point identical) a zero-filled buffer gives."""
+    import pointops
+    g = torch.Generator().manual_seed(sum(sizes) + distinct)
+    parts = []
+    for n in sizes:
+        base = torch.rand(distinct, 3, generator=g) * 4
+        parts.append(base[torch.randint(0, distinct, (n,), generator=g)])
+    xyz = torch.cat(parts)
+    offset = torch.tensor(sizes, dtype=torch.int32).cumsum(0).int()
+    new_offset = torch.tensor([n // 4 for n in sizes], dtype=torch.int32).cumsum(0).int()
+    ref = oracle.farthest_point_sampling(xyz, offset, new_offset)
+    out = pointops.farthest_point_sampling(xyz.to(cuda), offset.to(cuda), new_offset.to(cuda))
+    assert torch.equal(out.cpu(), ref)
+
+
 def test_fps_streamed_large_scene(cuda, oracle):
     """> 131072 points in one scene: the streamed kernel; few samples so the oracle stays fast."""
     import pointops
