@@ -360,10 +360,17 @@ class Bottleneck(_Freezable, nn.Module):
         aw, bw = _bn_affine(t.linear_w[0])
         w1, b1w = _fold(t.linear_w[2], t.linear_w[3])
         oa, ob = _bn_affine(self.bn2)
-        params = FZ.pack_pt_layer_params(A, cvec, t.linear_p[3].weight, t.linear_p[3].bias, aw, bw, w1, b1w,
-                                         t.linear_w[5].weight, t.linear_w[5].bias, oa, ob)
+        pack = lambda bw_, ob_: FZ.pack_pt_layer_params(A, cvec, t.linear_p[3].weight, t.linear_p[3].bias, aw, bw_, w1, b1w,
+                                                        t.linear_w[5].weight, t.linear_w[5].bias, oa, ob_)
+        # The q / k / v biases can leave the GEMM (whose bias epilogue is a second pass over (n, 3c) in cuBLASLt):
+        #   k_j + bk - (q_i + bq) + p_r   enters relu(aw * . + bw)  ->  bw' = bw + aw (bk - bq)
+        #   sum_s w_s (v_j + bv + p_r) = sum_s w_s (v_j + p_r) + bv (softmax weights sum to 1)  ->  ob' = ob + oa bv
+        # valid when no neighbour slot is a placeholder (those group to ZERO rows, not to the bias), i.e. when
+        # every scene has at least nsample points; the caller checks that on the host and else keeps `params`.
+        bq, bk, bv = (x.detach().double() for x in (t.linear_q.bias, t.linear_k.bias, t.linear_v.bias))
         W3, b3 = _fold(self.linear3, self.bn3)
-        return dict(l1=(W1.t(), b1), wqkv_t=Wqkv.t(), bqkv=bqkv, params=params, w3_t=W3.t(), b3=b3)
+        return dict(l1=(W1.t(), b1), wqkv_t=Wqkv.t(), bqkv=bqkv, params=pack(bw, ob),
+                    params_nobias=pack(bw + aw * (bk - bq), ob + oa * bv), w3_t=W3.t(), b3=b3)
 
     def _frozen_ok(self, x) -> bool:
         t = self.transformer
@@ -375,9 +382,13 @@ class Bottleneck(_Freezable, nn.Module):
         if self._frozen_ok(identity):
             f = self.frozen()
             c = self.transformer.out_planes
-            qkv = torch.addmm(f["bqkv"], _linear_act(f["l1"], identity), f["wqkv_t"])        # (n, 3c)
+            h = _linear_act(f["l1"], identity)
+            if min(C.scene_sizes(cloud.o_host)) >= self.transformer.nsample:   # no placeholder neighbours: biases folded
+                qkv, params = torch.mm(h, f["wqkv_t"]), f["params_nobias"]                    # (n, 3c)
+            else:
+                qkv, params = torch.addmm(f["bqkv"], h, f["wqkv_t"]), f["params"]
             y = FZ.pt_layer_forward(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], cloud.p, cloud.knn(self.transformer.nsample),
-                                    f["params"], out_affine=True)                             # ... bn2 + relu
+                                    params, out_affine=True)                                  # ... bn2 + relu
             z = torch.addmm(identity, y, f["w3_t"])                                           # skip + linear3 (bn3 scale folded)
             return cloud.with_feat(FZ.affine_act(z, None, f["b3"], None, relu=True, inplace=True))
         x = self.relu(self.bn1(self.linear1(cloud.x)))

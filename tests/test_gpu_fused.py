@@ -127,14 +127,17 @@ def test_interpolation_add_and_affine_act(cuda):
 
 
 @pytest.mark.parametrize("method", ["msp", "pdf"])
-def test_frozen_model_matches_unfrozen(cuda, method):
-    """The folded / fused inference form against the same model run module by module (eval)."""
+@pytest.mark.parametrize("sizes", [[9000, 5000], [9000, 600]])
+def test_frozen_model_matches_unfrozen(cuda, method, sizes):
+    """The folded / fused inference form against the same model run module by module (eval).
+    [9000, 600]: the small scene has fewer than nsample points from the third level on, so those levels
+    see placeholder neighbours and must keep the q / k / v biases in the GEMM (ptv1.Bottleneck._freeze)."""
     from pointcloudpdf_b200 import ptv1, synthetic as S
     torch.manual_seed(2024)
     net = ptv1.OpenSegPTv1(in_channels=6, num_classes=13, method=method)
     randomise_bn(net, torch.Generator().manual_seed(1))
     net = net.to(cuda).eval()
-    batch = S.s3dis_batch([9000, 5000], seed=3)
+    batch = S.s3dis_batch(sizes, seed=3)
     d = dict(coord=batch["coord"].to(cuda), feat=batch["feat"].to(cuda), offset=batch["offset"].to(cuda))
     outs = {}
     for frozen in (True, False):
