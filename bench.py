@@ -48,7 +48,7 @@ L2_FLUSH_BYTES = 256 << 20  # > 126 MB L2
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=N_POINTS)
@@ -69,7 +69,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.skip = index, None, [], 0
 
     def __enter__(self):
         try:
@@ -78,6 +78,10 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            t0 = time.time()   # NVML start-up (attach, first query) happens before the caller starts its clock
+            while not self.lines and time.time() - t0 < 3.0 and self.proc.poll() is None:
+                time.sleep(0.01)
+            self.skip = len(self.lines)
         except OSError:
             self.proc = None
         return self
@@ -98,7 +102,7 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[min(self.skip, max(len(self.lines) - 1, 0)):]:   # samples taken under load
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -167,6 +171,69 @@ def run_reference_arm(args):
             "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------ operator-level lines (cfg1) --
+
+def ops_cfg1(dev, hbm_peak):
+    """The second half of BASELINE.json's metric -- "kNN + group + aggregate GB/s vs HBM peak" -- on
+    configs[0]'s shape: one 24 000-point S3DIS-shaped cloud, k = 16, C = 32, share_planes = 8.  Each
+    operator is launched 24 times back to back (one CUDA graph, so no host gaps) over 8 rotating argument
+    sets (~60 MB each, > L2 in total) between two CUDA events; GB/s = SURVEY.md 8(d) algorithmic bytes /
+    mean time per launch."""
+    from pointcloudpdf_b200 import synthetic as S
+    import pointcloudpdf_b200.pointops as pointops
+    n, k, c, wc = 24000, 16, 32, 4
+    b = S.s3dis_batch([n], seed=2025)
+    xyz, off = b["coord"].to(dev), b["offset"].to(dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    idx, _ = pointops.knn_query(k, xyz, off)
+    sets = [dict(xyz=xyz.clone(), feat=torch.randn(n, c, device=dev, generator=g),
+                 pos=torch.randn(n, k, c, device=dev, generator=g), w=torch.randn(n, k, wc, device=dev, generator=g))
+            for _ in range(8)]
+
+    def timed(fn, reps=24):
+        for a in sets[:2]:
+            fn(a)
+        torch.cuda.synchronize()
+        st = torch.cuda.Stream(device=dev)
+        graph = torch.cuda.CUDAGraph()   # back-to-back launches without host gaps (SURVEY.md 8d)
+        with torch.cuda.graph(graph, stream=st, capture_error_mode="thread_local"):
+            for r in range(reps):
+                fn(sets[r % len(sets)])
+        times = []
+        with torch.cuda.stream(st):
+            graph.replay()
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                graph.replay()
+                e1.record(st)
+                e1.synchronize()
+                times.append(e0.elapsed_time(e1))
+        return statistics.median(times) / reps * 1e-3
+
+    def knn(a):
+        pointops.clear_caches()
+        pointops.knn_query(k, a["xyz"], off)
+
+    out = {}
+    with torch.no_grad():
+        for name, fn, nbytes, flops in (
+                ("knn_query k=16 (grid build + query)", knn, 12 * n + 12 * n + 8 * k * n, 8 * n * n),
+                ("grouping with_xyz (knn_query_and_group's gather)", lambda a: pointops.grouping(idx, a["feat"], xyz, xyz, with_xyz=True),
+                 4 * (n * c + 3 * n + 3 * n + n * k + n * k * (3 + c)), 0),
+                ("grouping2 (feature gather)", lambda a: pointops.grouping2(a["feat"], idx), 4 * (n * c + n * k + n * k * c), 0),
+                ("aggregation forward", lambda a: pointops.aggregation(a["feat"], a["pos"], a["w"], idx),
+                 4 * (n * c + n * k * c + n * k * wc + n * k + n * c), 0)):
+            sec = timed(fn)
+            out[name] = {"us": sec * 1e6, "alg_MB": nbytes / 1e6, "GBps": nbytes / sec / 1e9,
+                         "frac_of_hbm_peak": nbytes / sec / 1e9 / hbm_peak}
+            if flops:
+                out[name]["bruteforce_equivalent_TFLOPs"] = flops / sec / 1e12
+    pointops.clear_caches()
+    return {"shape": "N=24000, k=16, C=32, w_c=4 (BASELINE configs[0])",
+            "timing": "a CUDA graph of 24 back-to-back launches over 8 rotating argument sets, CUDA events around a replay, median of 5", "ops": out}
 
 
 # ------------------------------------------------------------------------------- B200 arm --
@@ -324,13 +391,41 @@ def main():
                              "share_of_step": d["ms"] / ms_profiled, "alg_MB_per_call": d["alg_bytes"] / d["calls"] / 1e6,
                              "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
                              "alg_GFLOP_per_call": d["alg_flops"] / d["calls"] / 1e9}
-        top = next(iter(kernels)) if kernels else None
+        # FPS is the largest kernel by time but it is a serial dependent chain on 16 SMs (latency-bound: no
+        # byte or flop roofline describes it; its accounting is reported as `dominant_kernel`).  `roofline`
+        # is the largest bandwidth-class kernel of the step: the fused group + aggregate layer.
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        except (OSError, ValueError):
+            pass
+        bw_class = [k for k in kernels if k not in ("pob_farthest_point_sampling", "pob_knn_grid_query", "pob_knn_grid_build")]
+        top = bw_class[0] if bw_class else None
         roof = None
         if top:
             kd = kernels[top]
+            tr = traffic.get(top, {})
             roof = {"kernel": top, "bound": "hbm", "achieved": kd["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kd["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
-                    "share_of_step": kd["share_of_step"], "avg_launch_ms": kd["ms_per_step"] / kd["calls_per_step"]}
+                    "frac": kd["frac_of_hbm_peak"], "traffic": tr.get("dram_bytes_per_launch"),
+                    "traffic_source": tr.get("source"), "peak_source": peak_src,
+                    "share_of_step": kd["share_of_step"], "avg_launch_ms": kd["ms_per_step"] / kd["calls_per_step"],
+                    "alg_bytes_per_launch": kd["alg_MB_per_call"] * 1e6,
+                    "note": "achieved = compulsory bytes of the FUSED op (q, k, v, out rows, indices, coordinates once) / "
+                            "mean launch time by CUDA events in the instrumented pass; the (n, ns, C) tensors the unfused "
+                            "reference ops would move are never materialised, so the kernel is bound by L2 gathers and FP32 "
+                            "issue, not HBM (profiles/)"}
+        dominant = None
+        if kernels:
+            name = next(iter(kernels))
+            kd = kernels[name]
+            clk = (clocks.summary().get("sm_mhz") or 1965.0) * 1e6
+            fp32_peak = 148 * 128 * 2 * clk / 1e12
+            tf = kd["alg_GFLOP_per_call"] / (kd["ms_per_step"] / kd["calls_per_step"]) if kd["ms_per_step"] > 0 else 0.0
+            dominant = {"kernel": name, "bound": "latency (serial chain; FP32 CUDA cores)", "share_of_step": kd["share_of_step"],
+                        "avg_launch_ms": kd["ms_per_step"] / kd["calls_per_step"],
+                        "bruteforce_equivalent_TFLOPs": tf, "fp32_peak_TFLOPs": fp32_peak, "frac_of_fp32_peak": tf / fp32_peak,
+                        "note": "exact pruning skips ~95 % of the distance updates the flop count assumes; the kernel runs on "
+                                "one 16-CTA cluster and overlaps other rooms' kernels (share_of_step can exceed 1)"}
         h2d = sum(v.numel() * v.element_size() for v in host[0].values())
         d2h = score.numel() * score.element_size() + pred.numel() * pred.element_size()
         line = {"metric": METRIC, "value": world * args.points * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -354,7 +449,8 @@ def main():
                 "kernel_attribution": {"how": "second pass of the same K steps, launched eagerly (no graph replay), with CUDA events around every C-ABI call; "
                                               "with rooms in flight concurrently, kernel times overlap and shares can sum past 1",
                                        "ms_per_step_instrumented": ms_profiled / K},
-                "roofline": roof, "kernels": kernels, "clocks": clocks.summary()}
+                "roofline": roof, "dominant_kernel": dominant, "kernels": kernels, "clocks": clocks.summary()}
+        line["ops_cfg1"] = ops_cfg1(dev, hbm_peak)
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n = args.cpu_sample_points
