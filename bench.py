@@ -72,9 +72,11 @@ class ClockSampler:
         self.index, self.proc, self.lines, self.skip = index, None, [], 0
 
     def __enter__(self):
+        if self.index is None:   # only rank 0 polls NVML: N concurrent nvidia-smi loops contend on the driver lock
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -323,7 +325,7 @@ def main():
     # ---- value: device-resident inputs, K steps, CUDA events on the main stream ----
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local if rank == 0 else None) as clocks:
         barrier()
         e0.record()
         if depth > 1:

@@ -513,11 +513,28 @@ fps_chain_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
     if (C > 1) cluster.sync();  // nobody leaves while a peer may still be writing into its shared memory
 }
 
-// Same algorithm with the points left in global memory (L2-resident for any realistic scene):
-// the fallback for scenes that do not fit the register-resident kernel.
+// Scenes too large for the register-resident kernels: the same algorithm with the points left in global
+// memory (L2-resident for any realistic scene) and the SAME exact pruning, per tile of 256 points.  A warp
+// owns every 512th tile of the scene's point sequence (cell order when the kNN grid is given: compact
+// tiles); per tile it keeps {bbox, max min-distance, argmax index, argmax coordinates} in shared memory.
+// An iteration tests the new sample against the tile boxes and touches only tiles it can change (a few
+// per cent), so what is left is the per-iteration synchronisation: warp -> CTA -> cluster argmax.
+// tmp (caller's buffer, n floats) holds the running min-distances in the kernel's point order.
+constexpr int FPS_TILE_PTS = 8;                        // points per lane per tile
+constexpr int FPS_TILE = 32 * FPS_TILE_PTS;            // 256 points
+constexpr int FPS_STREAM_WARPS = FPS_STREAM_THREADS / 32;
+struct __align__(16) FpsTileRec {
+    float lo[3], hi[3];
+    unsigned bits;   // float bits of the tile's maximum min-distance
+    int idx;         // lowest original index attaining it
+    float x, y, z;   // its coordinates
+    int pad;
+};
+
 __global__ void __launch_bounds__(FPS_STREAM_THREADS, 1)
 fps_stream_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
-                  float* __restrict__ tmp, int* __restrict__ idx) {
+                  const SceneGrid* __restrict__ scenes, const int* __restrict__ cell_start,
+                  const float4* __restrict__ sorted, float* __restrict__ tmp, int* __restrict__ idx, int max_tiles_per_warp) {
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -525,50 +542,181 @@ fps_stream_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s_n = scene == 0 ? 0 : offset[scene - 1], e_n = offset[scene];
     const int s_m = scene == 0 ? 0 : new_offset[scene - 1], e_m = new_offset[scene];
-    __shared__ unsigned s_bits[32];
-    __shared__ int s_idx[32];
-    __shared__ FpsMsg s_msg[2][FPS_MAX_CLUSTER];
-    if (e_m <= s_m || e_n <= s_n) return;
+    extern __shared__ __align__(16) unsigned char fps_stream_smem[];
+    FpsTileRec* recs = reinterpret_cast<FpsTileRec*>(fps_stream_smem) + (size_t)warp * max_tiles_per_warp;
+    __shared__ unsigned s_bits[2][FPS_STREAM_WARPS];   // per-warp entries, double-buffered by iteration parity
+    __shared__ int s_idx[2][FPS_STREAM_WARPS];
+    __shared__ float s_c[2][FPS_STREAM_WARPS][3];
+    __shared__ __align__(16) FpsMsg s_msg[2][FPS_MAX_CLUSTER];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    if (e_m <= s_m || e_n <= s_n) return;   // uniform over the cluster
 
-    const int stride = C * FPS_STREAM_THREADS;
-    const int first = s_n + rank * FPS_STREAM_THREADS + tid;
-    for (int i = first; i < e_n; i += stride) tmp[i] = PLACEHOLDER_D2;
+    const int n = e_n - s_n;
+    const bool in_cells = scenes != nullptr && scenes[scene].use_grid;
+    const int sbase = in_cells ? __ldg(cell_start + scenes[scene].cell_base) : 0;
+    const int ntiles = (n + FPS_TILE - 1) / FPS_TILE;
+    const int gw = rank * FPS_STREAM_WARPS + warp, nw = C * FPS_STREAM_WARPS;
+    const int my_tiles = gw < ntiles ? (ntiles - gw + nw - 1) / nw : 0;
+    float* tm = tmp + s_n;
+
+    auto load_point = [&](int pos, float& x, float& y, float& z, int& gi) {
+        if (in_cells) {
+            const float4 v = __ldg(sorted + sbase + pos);
+            x = v.x; y = v.y; z = v.z; gi = __float_as_int(v.w);
+        } else {
+            const int i = s_n + pos;
+            x = __ldg(xyz + (int64_t)i * 3); y = __ldg(xyz + (int64_t)i * 3 + 1); z = __ldg(xyz + (int64_t)i * 3 + 2);
+            gi = i;
+        }
+    };
+    // (re)compute one tile against a sample (first = true: initialise instead) and refresh its record
+    auto visit = [&](int j, bool first, float ox, float oy, float oz) {
+        const int base = (gw + j * nw) * FPS_TILE;
+        float bd = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
+        int bi = INT_MAX;
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        bool finite = true;
+#pragma unroll
+        for (int p = 0; p < FPS_TILE_PTS; p++) {
+            const int pos = base + p * 32 + lane;
+            if (pos < n) {
+                float x, y, z; int gi;
+                load_point(pos, x, y, z, gi);
+                float t;
+                if (first) {
+                    t = PLACEHOLDER_D2;
+                    tm[pos] = t;
+                    finite = finite && isfinite(x) && isfinite(y) && isfinite(z);
+                    lo[0] = fminf(lo[0], x); hi[0] = fmaxf(hi[0], x);
+                    lo[1] = fminf(lo[1], y); hi[1] = fmaxf(hi[1], y);
+                    lo[2] = fminf(lo[2], z); hi[2] = fmaxf(hi[2], z);
+                } else {
+                    const float old = tm[pos];
+                    t = fminf(d2_ref(x, y, z, ox, oy, oz), old);
+                    if (t != old) tm[pos] = t;
+                }
+                if (t > bd || (t == bd && gi < bi)) { bd = t; bi = gi; bx = x; by = y; bz = z; }
+            }
+        }
+        const unsigned mybits = bd >= 0.f ? __float_as_uint(bd) : 0u;
+        const unsigned wbits = __reduce_max_sync(FULL, mybits);
+        const int wi = __reduce_min_sync(FULL, (bd >= 0.f && mybits == wbits) ? bi : INT_MAX);
+        const unsigned own = __ballot_sync(FULL, bd >= 0.f && mybits == wbits && bi == wi);
+        const int ol = own ? __ffs(own) - 1 : 0;
+        const float wx = __shfl_sync(FULL, bx, ol), wy = __shfl_sync(FULL, by, ol), wz = __shfl_sync(FULL, bz, ol);
+        if (first) {
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    lo[a] = fminf(lo[a], __shfl_xor_sync(FULL, lo[a], o));
+                    hi[a] = fmaxf(hi[a], __shfl_xor_sync(FULL, hi[a], o));
+                }
+            if (!__all_sync(FULL, finite)) {   // a box that every sample "touches": pruning off for this tile
+#pragma unroll
+                for (int a = 0; a < 3; a++) { lo[a] = -FLT_MAX; hi[a] = FLT_MAX; }
+            }
+        }
+        if (lane == 0) {
+            FpsTileRec& r = recs[j];
+            if (first) {
+#pragma unroll
+                for (int a = 0; a < 3; a++) { r.lo[a] = lo[a]; r.hi[a] = hi[a]; }
+            }
+            r.bits = wbits; r.idx = wi; r.x = wx; r.y = wy; r.z = wz;
+        }
+    };
+
+    for (int j = 0; j < my_tiles; j++) visit(j, true, 0.f, 0.f, 0.f);
+    __syncwarp();
     float ox = __ldg(xyz + (int64_t)s_n * 3), oy = __ldg(xyz + (int64_t)s_n * 3 + 1), oz = __ldg(xyz + (int64_t)s_n * 3 + 2);
     if (rank == 0 && tid == 0) idx[s_m] = s_n;
 
-    for (int j = s_m + 1; j < e_m; j++) {
-        float best = 0.f;
-        int gi = INT_MAX;
-        for (int i = first; i < e_n; i += stride) {
-            const float d = d2_ref(__ldg(xyz + (int64_t)i * 3), __ldg(xyz + (int64_t)i * 3 + 1),
-                                   __ldg(xyz + (int64_t)i * 3 + 2), ox, oy, oz);
-            const float t = fminf(d, tmp[i]);
-            tmp[i] = t;
-            if (t > best || gi == INT_MAX) { best = t; gi = i; }
-        }
-        unsigned wbits; int wi;
-        warp_argmax(__float_as_uint(best), gi, wbits, wi);
-        if (lane == 0) { s_bits[warp] = wbits; s_idx[warp] = wi; }
-        __syncthreads();
-        unsigned cbits; int ci;
-        warp_argmax(s_bits[lane], s_idx[lane], cbits, ci);
-        const int par = j & 1;
-        if (warp == 0 && lane < C) {
-            FpsMsg msg = {cbits, ci, 0.f, 0.f, 0.f, 0, 0, 0};
-            if (ci != INT_MAX) {
-                msg.x = __ldg(xyz + (int64_t)ci * 3); msg.y = __ldg(xyz + (int64_t)ci * 3 + 1); msg.z = __ldg(xyz + (int64_t)ci * 3 + 2);
+    // exchange plumbing as in fps_cluster_kernel: st.async + mbarrier, NO cluster-scope fence on the chain
+    // (cluster.sync() would make every iteration wait for the tmp stores above to drain: ~2 us)
+    const unsigned bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]);
+    unsigned rslot0 = 0, rslot1 = 0, rbar0 = 0, rbar1 = 0;
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar0, C * (int)sizeof(FpsMsg));
+        mbar_expect_tx(bar1, C * (int)sizeof(FpsMsg));
+    }
+    if (warp == 0 && lane < C) {  // lane l talks to CTA l
+        rslot0 = mapa_u32(smem_u32(&s_msg[0][rank]), lane);
+        rslot1 = mapa_u32(smem_u32(&s_msg[1][rank]), lane);
+        rbar0 = mapa_u32(bar0, lane);
+        rbar1 = mapa_u32(bar1, lane);
+    }
+    cluster.sync();  // every CTA's barriers exist before anyone writes remotely
+
+    const int iters = e_m - s_m - 1;
+    for (int r = 0; r < iters; r++) {
+        const int par = r & 1;
+        // ---- tiles the new sample can change (exact, conservative; see fps_cluster_kernel) ----
+        for (int j0 = 0; j0 < my_tiles; j0 += 32) {
+            const int j = j0 + lane;
+            bool touch = false;
+            if (j < my_tiles) {
+                const FpsTileRec& rec = recs[j];
+                const float ex = fmaxf(fmaxf(rec.lo[0] - ox, ox - rec.hi[0]), 0.f);
+                const float ey = fmaxf(fmaxf(rec.lo[1] - oy, oy - rec.hi[1]), 0.f);
+                const float ez = fmaxf(fmaxf(rec.lo[2] - oz, oz - rec.hi[2]), 0.f);
+                const float b2 = __fmaf_rn(ez, ez, __fmaf_rn(ex, ex, __fmul_rn(ey, ey)));
+                touch = !(b2 * 0.99999f >= __uint_as_float(rec.bits));
             }
-            *cluster.map_shared_rank(&s_msg[par][rank], lane) = msg;
+            unsigned tmask = __ballot_sync(FULL, touch);
+            while (tmask) {
+                const int jj = j0 + __ffs(tmask) - 1;
+                tmask &= tmask - 1;
+                visit(jj, false, ox, oy, oz);
+            }
+            __syncwarp();
         }
-        cluster.sync();
+        // ---- warp argmax over its tile records ----
+        unsigned wb = 0u; int wi = INT_MAX, wj = 0;
+        for (int j0 = 0; j0 < my_tiles; j0 += 32) {
+            const int j = j0 + lane;
+            const unsigned b = j < my_tiles ? recs[j].bits : 0u;
+            const int i2 = j < my_tiles ? recs[j].idx : INT_MAX;
+            unsigned cb; int ci;
+            warp_argmax(b, i2, cb, ci);
+            if (cb > wb || (cb == wb && ci < wi)) {
+                const unsigned who = __ballot_sync(FULL, j < my_tiles && b == cb && i2 == ci);
+                wb = cb; wi = ci; wj = j0 + (who ? __ffs(who) - 1 : 0);
+            }
+        }
+        if (lane == 0) {
+            s_bits[par][warp] = wb; s_idx[par][warp] = wi;
+            const bool real = my_tiles > 0 && wi != INT_MAX;
+            s_c[par][warp][0] = real ? recs[wj].x : 0.f; s_c[par][warp][1] = real ? recs[wj].y : 0.f;
+            s_c[par][warp][2] = real ? recs[wj].z : 0.f;
+        }
+        __syncthreads();
+        // ---- CTA argmax (every warp redundantly), all-to-all of the CTA winners, cluster argmax ----
+        const unsigned eb = s_bits[par][lane];
+        const int ei = s_idx[par][lane];
+        unsigned cbits; int ci;
+        warp_argmax(eb, ei, cbits, ci);
+        const unsigned whow = __ballot_sync(FULL, eb == cbits && ei == ci);
+        const int wl0 = whow ? __ffs(whow) - 1 : 0;
+        if (warp == 0 && lane < C) {
+            const unsigned rs = par ? rslot1 : rslot0, rb = par ? rbar1 : rbar0;
+            st_async_v4(rs, cbits, (unsigned)ci, __float_as_uint(s_c[par][wl0][0]), __float_as_uint(s_c[par][wl0][1]), rb);
+            st_async_v4(rs + 16, __float_as_uint(s_c[par][wl0][2]), 0u, 0u, 0u, rb);
+        }
+        mbar_wait(par ? bar1 : bar0, (unsigned)(r >> 1) & 1u);
+        if (tid == 0) mbar_expect_tx(par ? bar1 : bar0, C * (int)sizeof(FpsMsg));  // re-arm for r + 2
         const FpsMsg mine = s_msg[par][lane < C ? lane : 0];
         unsigned gbits; int gidx;
         warp_argmax(lane < C ? mine.bits : 0u, lane < C ? mine.idx : INT_MAX, gbits, gidx);
         const unsigned who = __ballot_sync(FULL, lane < C && mine.idx == gidx);
         const int wl = who ? __ffs(who) - 1 : 0;
         ox = __shfl_sync(FULL, mine.x, wl); oy = __shfl_sync(FULL, mine.y, wl); oz = __shfl_sync(FULL, mine.z, wl);
-        if (rank == 0 && tid == 0) idx[j] = gidx;
+        if (rank == 0 && tid == 0) idx[s_m + 1 + r] = gidx;
     }
+    cluster.sync();  // nobody leaves while a peer may still be writing into its shared memory
 }
 
 static int launch_cluster(const void* kernel, int b, int C, int threads, size_t smem, cudaStream_t stream, void** args) {
@@ -662,8 +810,15 @@ POB_API int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, 
     const int64_t P = ceil_div(n_max, (int64_t)C * T);
     if (P > PMAX) {
         if (!tmp) return POB_ERR_BAD_ARG;
-        void* args[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&tmp, (void*)&idx};
-        return launch_cluster((const void*)fps_stream_kernel, b, 16, FPS_STREAM_THREADS, 0, stream, args);
+        const int Cs = 16;
+        const int64_t ntiles = ceil_div(n_max, (int64_t)FPS_TILE);
+        int tiles_per_warp = (int)ceil_div(ntiles, (int64_t)Cs * FPS_STREAM_WARPS);
+        if (tiles_per_warp < 1) tiles_per_warp = 1;
+        const size_t smem = sizeof(FpsTileRec) * (size_t)FPS_STREAM_WARPS * tiles_per_warp;
+        if (smem > 200 * 1024) return POB_ERR_UNSUPPORTED;   // > 17 M points in one scene
+        void* args[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&scenes, (void*)&cell_start,
+                        (void*)&sorted, (void*)&tmp, (void*)&idx, (void*)&tiles_per_warp};
+        return launch_cluster((const void*)fps_stream_kernel, b, Cs, FPS_STREAM_THREADS, smem, stream, args);
     }
     // POINTOPS_B200_FPS=single selects the one-sample-per-exchange kernel (A/B and fallback)
     static const bool use_chain = !(getenv("POINTOPS_B200_FPS") && strcmp(getenv("POINTOPS_B200_FPS"), "single") == 0);

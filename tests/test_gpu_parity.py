@@ -200,6 +200,18 @@ def test_fps_streamed_large_scene(cuda, oracle):
     assert torch.equal(out.cpu(), ref)
 
 
+@pytest.mark.parametrize("kind", ["room", "volume"])
+def test_fps_streamed_many_samples_and_mixed_batch(cuda, oracle, kind):
+    """The tile-pruned streamed kernel (scene > 131072 points) over thousands of dependent samples, in a
+    batch whose other scene is small (every scene of a launch runs the same kernel)."""
+    import pointops
+    xyz, offset = make_cloud([140000, 3000], 9, kind)
+    new_offset = torch.tensor([1500, 1500 + 750], dtype=torch.int32)
+    ref = oracle.farthest_point_sampling(xyz, offset, new_offset)
+    out = pointops.farthest_point_sampling(xyz.to(cuda), offset.to(cuda), new_offset.to(cuda))
+    assert torch.equal(out.cpu(), ref)
+
+
 # --------------------------------------------------------------- grouping (a3, a4, a8) --
 
 @pytest.mark.parametrize("c,ns,with_xyz,dtype", [
