@@ -70,6 +70,33 @@ int pob_knn_query_bruteforce(int64_t m, int nsample, int b, const float* xyz, co
                              const int* offset, const int* new_offset, int* idx, float* dist, int take_sqrt,
                              void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+/* ---------------------------------------------------------------- radius queries --------
+ * (off the PTv1 path; pointops.ball_query / random_ball_query are used by other Pointcept backbones and by
+ * PDF's pseudo-label neighbour graph)  Both run on a grid workspace built by
+ * pob_knn_grid_build for the same (xyz, offset, n, b, cell_pts); a point is accepted when
+ * d2 <= 1e-5 or min_radius^2 <= d2 < max_radius^2 (ball_query_cuda_kernel.cu:99).
+ *
+ * pob_ball_query replaces ball_query_cuda_launcher(m, nsample, min_radius, max_radius, xyz, new_xyz, offset,
+ * new_offset, idx, dist2) (src/ball_query/ball_query_cuda_kernel.h): the accepted points in ascending index
+ * order, passed through the reference's heap_sort exactly as the kernel does (no heapify first, so the list
+ * is only partially ordered by distance -- reproduced, not fixed); at most nsample of them -> that list,
+ * padded with idx -1 / dist2 1e10; more -> every (cnt / nsample)-th entry, and dist2 then holds the
+ * candidate INDEX as a float, as ball_query_cuda_kernel.cu:120 writes it.
+ * *overflow_flag (device int, caller-zeroed) is set when a query saw more than 2048 candidates -- the size of
+ * the reference's per-thread stack arrays, which it overruns; such rows use the first 2048 found.
+ *
+ * pob_random_ball_query replaces random_ball_query_cuda_launcher(m, nsample, min_radius, max_radius, order,
+ * xyz, new_xyz, offset, new_offset, idx, dist2) (src/random_ball_query/random_ball_query_cuda_kernel.h):
+ * the first nsample accepted points in the order of the permutation `order` (n global row indices, each
+ * scene's rows permuted within the scene); inv_scratch (n ints) is caller-owned scratch; nsample <= 256. */
+int pob_ball_query(int64_t m, int nsample, float min_radius, float max_radius, int64_t n, int b, const float* xyz,
+                   const float* new_xyz, const int* new_offset, float cell_pts, const void* workspace, int* idx,
+                   float* dist2, int* overflow_flag, cudaStream_t stream);
+int pob_random_ball_query(int64_t m, int nsample, float min_radius, float max_radius, int64_t n, int b,
+                          const int* order, const float* xyz, const float* new_xyz, const int* new_offset,
+                          float cell_pts, const void* workspace, int* inv_scratch, int* idx, float* dist2,
+                          cudaStream_t stream);
+
 /* ------------------------------------------------------- farthest point sampling -------
  * Replaces farthest_point_sampling_cuda_launcher(b, n, xyz, offset, new_offset, tmp, idx)
  * (src/sampling/sampling_cuda_kernel.h:13; kernel sampling_cuda_kernel.cu:15-129).
@@ -191,6 +218,28 @@ int pob_transition_down_pool(int64_t m, int nsample, int c, const float* z, cons
  * (point_transformer_seg.py:168-170); base may be NULL.                                             */
 int pob_interpolation_add_forward(int64_t n, int c, int k, const float* input, const int* idx, const float* weight,
                                   const float* base, float* output, cudaStream_t stream);
+
+/* ------------------------------------------------------- grouped vector attention steps --
+ * (off the PTv1 path: Point Transformer v2's operators)  Replace the four launchers of
+ * src/attention/attention_cuda_kernel.h with the same argument order:
+ *   relation   output[r, g]          = sum_c query[it[r], g, c] * key[ir[r], g, c] * weight[c]     (written)
+ *   fusion     output[it[r], g, c]  += weight[r, g] * value[ir[r], g, c]                           (accumulated)
+ * query / key / value (n, g, c), weight (c) resp. (m, g), index_target / index_refer (m) int32.
+ * Backward: grad_query, grad_key, grad_value and relation's grad_weight (c) are accumulated into (the caller
+ * zeroes them, as the reference's wrappers do); fusion's grad_weight (m, g) is written.                 */
+int pob_attention_relation_step_forward(int64_t m, int g, int c, const float* query, const float* key,
+                                        const float* weight, const int* index_target, const int* index_refer,
+                                        float* output, cudaStream_t stream);
+int pob_attention_relation_step_backward(int64_t m, int g, int c, const float* query, float* grad_query,
+                                         const float* key, float* grad_key, const float* weight, float* grad_weight,
+                                         const int* index_target, const int* index_refer, const float* grad_output,
+                                         cudaStream_t stream);
+int pob_attention_fusion_step_forward(int64_t m, int g, int c, const float* weight, const float* value,
+                                      const int* index_target, const int* index_refer, float* output,
+                                      cudaStream_t stream);
+int pob_attention_fusion_step_backward(int64_t m, int g, int c, const float* weight, float* grad_weight,
+                                       const float* value, float* grad_value, const int* index_target,
+                                       const int* index_refer, const float* grad_output, cudaStream_t stream);
 
 /* ------------------------------------------ fused open-set scoring (additive entry point) --
  * One pass over logits (n, K) [+ conf (n)] replacing

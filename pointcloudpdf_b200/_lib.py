@@ -29,6 +29,8 @@ SIGNATURES = {
     "pob_knn_grid_query": (I, [L, I, L, I, P, P, P, F, P, P, P, P, I, P]),
     "pob_knn_query": (I, [L, I, L, I, P, P, P, P, P, P, I, P, Z, P]),
     "pob_knn_query_bruteforce": (I, [L, I, I, P, P, P, P, P, P, I, P, Z, P]),
+    "pob_ball_query": (I, [L, I, F, F, L, I, P, P, P, F, P, P, P, P, P]),
+    "pob_random_ball_query": (I, [L, I, F, F, L, I, P, P, P, P, F, P, P, P, P, P]),
     "pob_fps_set_stats": (I, [P]),
     "pob_farthest_point_sampling": (I, [I, L, P, P, P, P, P, I, P, L, F, P]),
     "pob_grouping_forward": (I, [L, I, I, P, P, P, P]),
@@ -48,6 +50,10 @@ SIGNATURES = {
     "pob_affine_act": (I, [L, I, P, P, P, P, I, P, P]),
     "pob_transition_down_pool": (I, [L, I, I, P, P, P, P, P, P, P, P, P]),
     "pob_interpolation_add_forward": (I, [L, I, I, P, P, P, P, P, P]),
+    "pob_attention_relation_step_forward": (I, [L, I, I, P, P, P, P, P, P, P]),
+    "pob_attention_relation_step_backward": (I, [L, I, I, P, P, P, P, P, P, P, P, P, P]),
+    "pob_attention_fusion_step_forward": (I, [L, I, I, P, P, P, P, P, P]),
+    "pob_attention_fusion_step_backward": (I, [L, I, I, P, P, P, P, P, P, P, P]),
     "pob_score_workspace_bytes": (Z, [I]),
     "pob_score_fused": (I, [L, I, I, P, P, P, F, P, P, P, P, P, P, P, P, P, Z, P]),
 }

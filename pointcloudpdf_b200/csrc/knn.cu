@@ -453,6 +453,230 @@ __global__ void __launch_bounds__(256) knn_grid_kernel(int64_t m, int k, int b, 
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// Radius queries (pointops.ball_query / random_ball_query; off the PTv1 path) on
+// the same grid: one warp per query scans the cube of cells that covers the outer radius.
+
+// calls f(valid, point) once per batch of 32 candidates of the cube of radius R cells around (cx, cy, cz)
+template <class F>
+__device__ __forceinline__ void scan_cube(const SceneGrid& g, const int* __restrict__ cs, const float4* __restrict__ sorted,
+                                          int cx, int cy, int cz, int R, int lane, F&& f) {
+    const int x0 = max(cx - R, 0), x1 = min(cx + R, g.dx - 1);
+    const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dy - 1);
+    const int z0 = max(cz - R, 0), z1 = min(cz + R, g.dz - 1);
+    const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);
+    for (int rbase = 0; rbase < nrows; rbase += 32) {
+        const int row = rbase + lane;
+        int beg = 0, cnt = 0;
+        if (row < nrows) {
+            const int zz = z0 + row / ny, yy = y0 + row % ny;
+            const int c = (zz * g.dy + yy) * g.dx;
+            beg = __ldg(cs + c + x0);
+            cnt = __ldg(cs + c + x1 + 1) - beg;
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        const int shift = beg - (incl - cnt);
+        for (int obase = 0; obase < total; obase += 32) {
+            const int o = obase + lane;
+            int j = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(FULL, incl, j + step - 1);
+                if (v <= o) j += step;
+            }
+            const int pos = __shfl_sync(FULL, shift, j & 31) + o;
+            const bool valid = o < total;
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) p = __ldg(sorted + pos);
+            f(valid, p);
+        }
+    }
+}
+
+// cube radius (in cells) outside of which no point can have d2 < r2 (same bound as the kNN stop test)
+__device__ __forceinline__ int cover_radius(float r2, float h, int maxdim) {
+    int R = 1;
+    while (R < maxdim && !(bound2(R, h) > r2)) R++;
+    return R;
+}
+
+// the reference's acceptance test (ball_query_cuda_kernel.cu:99): the 1e-5 literal is a double
+__device__ __forceinline__ bool ball_accepts(float d2, float min_r2, float max_r2) {
+    return (double)d2 <= 1e-5 || (d2 >= min_r2 && d2 < max_r2);
+}
+
+constexpr int BALL_MAX_CAND = 2048;   // the reference's per-thread candi_dist[2048] / candi_idx[2048]
+constexpr int BALL_WARPS = 4;
+
+// ball_query_utils::reheap / heap_sort (ball_query_cuda_kernel.cu:16-42), literally.
+__device__ __forceinline__ void ref_heap_sort(float* dist, int* idx, int k) {
+    for (int i = k - 1; i > 0; i--) {
+        float td = dist[0]; dist[0] = dist[i]; dist[i] = td;
+        int ti = idx[0]; idx[0] = idx[i]; idx[i] = ti;
+        int root = 0, child = 1;
+        while (child < i) {
+            if (child + 1 < i && dist[child + 1] > dist[child]) child++;
+            if (dist[root] > dist[child]) break;
+            td = dist[root]; dist[root] = dist[child]; dist[child] = td;
+            ti = idx[root]; idx[root] = idx[child]; idx[child] = ti;
+            root = child;
+            child = 2 * root + 1;
+        }
+    }
+}
+
+// ball_query_cuda_kernel (ball_query_cuda_kernel.cu:58-124).  The reference appends the accepted points in
+// scan (= ascending index) order and then runs heap_sort on that list WITHOUT building a heap first, so its
+// output is only partially ordered by distance -- but it is a deterministic function of the index-ordered
+// list, and a drop-in has to return the same rows.  Hence: gather the candidates of the cube (any order),
+// put them in ascending index order (rank by counting), let one lane run the reference's heap_sort on the
+// shared-memory copy, then emit: up to nsample -> the list padded with (-1, 1e10); more -> every
+// (cnt / nsample)-th entry, with the candidate INDEX written into dist2 exactly as :120 does.
+__global__ void __launch_bounds__(BALL_WARPS * 32)
+ball_query_kernel(int64_t m, int nsample, float min_radius, float max_radius, int b, const float* __restrict__ xyz,
+                  const float* __restrict__ new_xyz, const int* __restrict__ new_offset,
+                  const SceneGrid* __restrict__ scenes, const int* __restrict__ cell_start,
+                  const float4* __restrict__ sorted, int* __restrict__ idx_out, float* __restrict__ dist2_out,
+                  int* __restrict__ overflow) {
+    extern __shared__ __align__(16) unsigned char ball_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* cd = reinterpret_cast<float*>(ball_smem) + (size_t)warp * 4 * BALL_MAX_CAND;   // per warp: cd | ci | sd | si
+    int* ci = reinterpret_cast<int*>(cd + BALL_MAX_CAND);
+    float* sd = cd + 2 * BALL_MAX_CAND;
+    int* si = reinterpret_cast<int*>(cd + 3 * BALL_MAX_CAND);
+    const int64_t q = (int64_t)blockIdx.x * BALL_WARPS + warp;
+    if (q >= m) return;
+    const int s = segment_of(q, new_offset, b);
+    const SceneGrid g = scenes[s];
+    const float qx = __ldg(new_xyz + q * 3), qy = __ldg(new_xyz + q * 3 + 1), qz = __ldg(new_xyz + q * 3 + 2);
+    const float max_r2 = __fmul_rn(max_radius, max_radius), min_r2 = __fmul_rn(min_radius, min_radius);
+    int cnt = 0;
+    auto offer = [&](bool valid, float d2, int i) {
+        const bool take = valid && ball_accepts(d2, min_r2, max_r2);
+        const unsigned mask = __ballot_sync(FULL, take);
+        const int at = cnt + __popc(mask & ((1u << lane) - 1u));
+        if (take && at < BALL_MAX_CAND) { cd[at] = d2; ci[at] = i; }
+        cnt += __popc(mask);
+    };
+    if (!g.use_grid) {
+        for (int base = g.start; base < g.end; base += 32) {
+            const int i = base + lane;
+            const bool valid = i < g.end;
+            float d2 = 0.f;
+            if (valid) d2 = d2_ref(qx, qy, qz, __ldg(xyz + (int64_t)i * 3), __ldg(xyz + (int64_t)i * 3 + 1),
+                                   __ldg(xyz + (int64_t)i * 3 + 2));
+            offer(valid, d2, i);
+        }
+    } else {
+        const int R = cover_radius(fmaxf(max_r2, 1.0001e-5f), g.h, MAX_DIM);
+        scan_cube(g, cell_start + g.cell_base, sorted, cell_coord(qx, g.lox, g.inv_h, g.dx),
+                  cell_coord(qy, g.loy, g.inv_h, g.dy), cell_coord(qz, g.loz, g.inv_h, g.dz), R, lane,
+                  [&](bool valid, const float4& p) { offer(valid, d2_ref(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w)); });
+    }
+    __syncwarp();
+    if (cnt > BALL_MAX_CAND) {   // the reference overruns its stack arrays here; report instead
+        if (lane == 0) atomicExch(overflow, 1);
+        cnt = BALL_MAX_CAND;
+    }
+    // ascending index order = the reference's scan order
+    for (int e = lane; e < cnt; e += 32) {
+        const int i = ci[e];
+        int rank = 0;
+        for (int f2 = 0; f2 < cnt; f2++) rank += ci[f2] < i ? 1 : 0;
+        sd[rank] = cd[e];
+        si[rank] = i;
+    }
+    __syncwarp();
+    if (lane == 0) ref_heap_sort(sd, si, cnt);
+    __syncwarp();
+    int* io = idx_out + q * nsample;
+    float* dout = dist2_out + q * nsample;
+    if (cnt <= nsample) {
+        for (int e = lane; e < nsample; e += 32) {
+            io[e] = e < cnt ? si[e] : -1;
+            dout[e] = e < cnt ? sd[e] : PLACEHOLDER_D2;
+        }
+    } else {
+        const float sep = (float)cnt / (float)nsample;
+        for (int e = lane; e < nsample; e += 32) {
+            const int j = (int)(sep * (float)e);
+            io[e] = si[j];
+            dout[e] = (float)si[j];
+        }
+    }
+}
+
+__global__ void invert_order_kernel(int64_t n, const int* __restrict__ order, int* __restrict__ inv) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const int i = order[p];
+        if (i >= 0 && i < n) inv[i] = (int)p;
+    }
+}
+
+// random_ball_query_cuda_kernel (random_ball_query_cuda_kernel.cu:58-107): the first nsample accepted points
+// in the order of the given permutation = the nsample accepted points with the smallest POSITION in
+// `order`: a top-k on the key (0, position) over the candidates of the cube.
+template <int KPL>
+__global__ void __launch_bounds__(256)
+random_ball_query_kernel(int64_t m, int nsample, float min_radius, float max_radius, int b, const int* __restrict__ order,
+                         const int* __restrict__ inv_order, const float* __restrict__ xyz,
+                         const float* __restrict__ new_xyz, const int* __restrict__ new_offset,
+                         const SceneGrid* __restrict__ scenes, const int* __restrict__ cell_start,
+                         const float4* __restrict__ sorted, int* __restrict__ idx_out, float* __restrict__ dist2_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= m) return;
+    const int s = segment_of(q, new_offset, b);
+    const SceneGrid g = scenes[s];
+    const float qx = __ldg(new_xyz + q * 3), qy = __ldg(new_xyz + q * 3 + 1), qz = __ldg(new_xyz + q * 3 + 2);
+    const float max_r2 = __fmul_rn(max_radius, max_radius), min_r2 = __fmul_rn(min_radius, min_radius);
+    TopK<KPL> t;
+#pragma unroll
+    for (int r = 0; r < KPL; r++) { t.d[r] = PLACEHOLDER_D2; t.i[r] = INT_MAX; }
+    float tau_d = PLACEHOLDER_D2;
+    int tau_i = INT_MAX;
+    auto offer = [&](bool valid, float d2, int i) {
+        const bool take = valid && ball_accepts(d2, min_r2, max_r2);
+        topk_offer<KPL>(t, nsample, tau_d, tau_i, take, 0.f, take ? __ldg(inv_order + i) : 0, lane);
+    };
+    if (!g.use_grid) {
+        for (int base = g.start; base < g.end; base += 32) {
+            const int i = base + lane;
+            const bool valid = i < g.end;
+            float d2 = 0.f;
+            if (valid) d2 = d2_ref(qx, qy, qz, __ldg(xyz + (int64_t)i * 3), __ldg(xyz + (int64_t)i * 3 + 1),
+                                   __ldg(xyz + (int64_t)i * 3 + 2));
+            offer(valid, d2, i);
+        }
+    } else {
+        const int R = cover_radius(fmaxf(max_r2, 1.0001e-5f), g.h, MAX_DIM);
+        scan_cube(g, cell_start + g.cell_base, sorted, cell_coord(qx, g.lox, g.inv_h, g.dx),
+                  cell_coord(qy, g.loy, g.inv_h, g.dy), cell_coord(qz, g.loz, g.inv_h, g.dz), R, lane,
+                  [&](bool valid, const float4& p) { offer(valid, d2_ref(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w)); });
+    }
+#pragma unroll
+    for (int r = 0; r < KPL; r++) {
+        const int e = r * 32 + lane;
+        if (e < nsample) {
+            const bool real = t.i[r] != INT_MAX;
+            int i = -1;
+            float d2 = PLACEHOLDER_D2;
+            if (real) {
+                i = __ldg(order + t.i[r]);
+                d2 = d2_ref(qx, qy, qz, __ldg(xyz + (int64_t)i * 3), __ldg(xyz + (int64_t)i * 3 + 1), __ldg(xyz + (int64_t)i * 3 + 2));
+            }
+            idx_out[q * nsample + e] = i;
+            dist2_out[q * nsample + e] = d2;
+        }
+    }
+}
+
 }  // namespace pob
 
 using namespace pob;
@@ -567,4 +791,55 @@ POB_API int pob_knn_query_bruteforce(int64_t m, int nsample, int b, const float*
     pob_count_launches(1);
     return knn_launch(m, nsample, b, xyz, new_xyz, new_offset, scenes, nullptr, nullptr, idx, dist, nullptr, take_sqrt,
                       1, stream);
+}
+
+// ball_query_cuda_launcher(m, nsample, min_radius, max_radius, xyz, new_xyz, offset, new_offset, idx, dist2)
+// (src/ball_query/ball_query_cuda_kernel.h) on a grid workspace built by pob_knn_grid_build for (xyz, offset).
+// dist2 receives what the reference writes (d2, or the candidate index where it subsamples, see the kernel).
+// *overflow_flag (device int, caller-zeroed, may be NULL) is set when a query had more than 2048 candidates,
+// where the reference overruns its stack arrays; such rows use the first 2048 found.
+POB_API int pob_ball_query(int64_t m, int nsample, float min_radius, float max_radius, int64_t n, int b, const float* xyz,
+                           const float* new_xyz, const int* new_offset, float cell_pts, const void* workspace, int* idx,
+                           float* dist2, int* overflow_flag, cudaStream_t stream) {
+    if (m < 0 || nsample < 1 || b < 1 || !workspace || !(min_radius < max_radius)) return POB_ERR_BAD_ARG;
+    if (m == 0) return 0;
+    if (!xyz || !new_xyz || !new_offset || !idx || !dist2 || !overflow_flag) return POB_ERR_BAD_ARG;
+    if (!(cell_pts >= 0.25f)) cell_pts = 0.25f;
+    const GridLayout L = grid_layout(n, b, cell_pts);
+    const char* ws = (const char*)workspace;
+    const size_t smem = 4 * sizeof(float) * BALL_WARPS * BALL_MAX_CAND;   // candidates + index-ordered copy, 32 KB per warp
+    POB_CHECK(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ball_query_kernel<<<(unsigned)ceil_div(m, BALL_WARPS), BALL_WARPS * 32, smem, stream>>>(
+        m, nsample, min_radius, max_radius, b, xyz, new_xyz, new_offset, (const SceneGrid*)(ws + L.off_scene),
+        (const int*)(ws + L.off_start), (const float4*)(ws + L.off_sorted), idx, dist2, overflow_flag);
+    pob_count_launches(1);
+    POB_RETURN_LAST_ERROR();
+}
+
+// random_ball_query_cuda_launcher(m, nsample, min_radius, max_radius, order, xyz, new_xyz, offset, new_offset,
+// idx, dist2) (src/random_ball_query/random_ball_query_cuda_kernel.h).  order (n): a permutation of each
+// scene's rows (global indices, scene-major); inv_scratch (n ints, caller-owned) receives its inverse.
+POB_API int pob_random_ball_query(int64_t m, int nsample, float min_radius, float max_radius, int64_t n, int b,
+                                  const int* order, const float* xyz, const float* new_xyz, const int* new_offset,
+                                  float cell_pts, const void* workspace, int* inv_scratch, int* idx, float* dist2,
+                                  cudaStream_t stream) {
+    if (m < 0 || nsample < 1 || nsample > 256 || b < 1 || !workspace || !(min_radius < max_radius)) return POB_ERR_BAD_ARG;
+    if (m == 0) return 0;
+    if (!order || !xyz || !new_xyz || !new_offset || !inv_scratch || !idx || !dist2) return POB_ERR_BAD_ARG;
+    if (!(cell_pts >= 0.25f)) cell_pts = 0.25f;
+    const GridLayout L = grid_layout(n, b, cell_pts);
+    const char* ws = (const char*)workspace;
+    invert_order_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(n, order, inv_scratch);
+    const unsigned blocks = (unsigned)ceil_div(m, 8);
+#define POB_RBQ(KPL)                                                                                                  \
+    random_ball_query_kernel<KPL><<<blocks, 256, 0, stream>>>(m, nsample, min_radius, max_radius, b, order, inv_scratch, \
+        xyz, new_xyz, new_offset, (const SceneGrid*)(ws + L.off_scene), (const int*)(ws + L.off_start),                \
+        (const float4*)(ws + L.off_sorted), idx, dist2)
+    if (nsample <= 32) POB_RBQ(1);
+    else if (nsample <= 64) POB_RBQ(2);
+    else if (nsample <= 128) POB_RBQ(4);
+    else POB_RBQ(8);
+#undef POB_RBQ
+    pob_count_launches(2);
+    POB_RETURN_LAST_ERROR();
 }

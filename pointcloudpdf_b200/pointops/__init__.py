@@ -5,13 +5,13 @@ hand-written sm_100a kernel from libpointops_b200.so (no Triton, no CPU fallback
 pointops2 spellings used by BASELINE.json's north_star (furthestsampling, knnquery,
 queryandgroup; libs/pointops2/functions/pointops.py:34,56,964) are provided as aliases.
 """
-from .query import knn_query, ball_query, random_ball_query, KNNQuery
+from .query import knn_query, ball_query, random_ball_query, KNNQuery, BallQuery, RandomBallQuery
 from .sampling import farthest_point_sampling, FarthestPointSampling
 from .grouping import grouping, grouping2, Grouping, grouping_split
 from .interpolation import interpolation, interpolation2, Interpolation
 from .subtraction import subtraction, Subtraction
 from .aggregation import aggregation, Aggregation
-from .attention import attention_relation_step, attention_fusion_step
+from .attention import attention_relation_step, attention_fusion_step, AttentionRelationStep, AttentionFusionStep
 from .utils import (
     query_and_group,
     knn_query_and_group,

@@ -21,7 +21,7 @@ def knn_query_and_group(feat, xyz, offset=None, new_xyz=None, new_offset=None, i
 
 def ball_query_and_group(feat, xyz, offset=None, new_xyz=None, new_offset=None, idx=None, max_radio=None,
                          min_radio=0, nsample=None, with_xyz=False):
-    """functions/utils.py:21-39 (needs ball_query when idx is None: not on the PTv1 path)."""
+    """functions/utils.py:21-39: ball query (unless idx is given) + gather with -1 masking."""
     if idx is None:
         idx, _ = ball_query(nsample, max_radio, min_radio, xyz, offset, new_xyz, new_offset)
     return grouping(idx, feat, xyz, new_xyz, with_xyz), idx

@@ -172,3 +172,28 @@ def test_reference_wrappers_live(oracle):
     assert torch.equal(idx, ridx) and torch.equal(dist, rdist)
     assert torch.equal(oracle.grouping(idx, feat, xyz, xyz, True), rg)
     assert torch.equal(oracle.farthest_point_sampling(xyz, offset, new_offset), rf)
+
+
+def test_radius_query_restatements_closed_forms(oracle):
+    """ball_query / random_ball_query restatements on cases with known answers."""
+    xyz = torch.tensor([[0, 0, 0], [1, 0, 0], [2, 0, 0], [3, 0, 0], [10, 0, 0]], dtype=torch.float32)
+    offset = torch.tensor([5], dtype=torch.int32)
+    S = lambda *a: oracle.ball_query_dist2(*a, order="sorted")
+    idx, d2 = S(4, 2.5, 0.0, xyz, offset)
+    assert idx[0].tolist() == [0, 1, 2, -1] and d2[0].tolist() == [0.0, 1.0, 4.0, 1e10]
+    assert idx[4].tolist() == [4, -1, -1, -1]
+    # inner radius: the query itself (d2 <= 1e-5) is always accepted
+    idx, _ = S(4, 2.5, 1.5, xyz, offset)
+    assert idx[0].tolist() == [0, 2, -1, -1]
+    # more candidates than nsample: every (cnt / nsample)-th of the list, "dist2" = the index (reference quirk)
+    idx, d2 = S(2, 3.5, 0.0, xyz, offset)
+    assert idx[0].tolist() == [0, 2] and d2[0].tolist() == [0.0, 2.0]
+    # the reference's mechanics (default): heap_sort on the un-heapified scan-ordered list [0, 1, 4] -> [1, 4, 0]
+    idx, dist = oracle.ball_query(4, 2.5, 0.0, xyz, offset)
+    assert idx[0].tolist() == [1, 2, 0, -1] and dist[0].tolist() == [1.0, 2.0, 0.0, 1e5]
+    # random ball query with the identity order = first nsample accepted rows in index order
+    order = torch.arange(5, dtype=torch.int32)
+    ridx, rd2 = oracle.random_ball_query_dist2(2, 3.5, 0.0, order, xyz, offset)
+    assert ridx[3].tolist() == [0, 1] and rd2[3].tolist() == [9.0, 4.0]
+    ridx, _ = oracle.random_ball_query_dist2(2, 3.5, 0.0, torch.tensor([4, 3, 2, 1, 0], dtype=torch.int32), xyz, offset)
+    assert ridx[3].tolist() == [3, 2]
