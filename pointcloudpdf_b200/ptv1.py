@@ -691,7 +691,13 @@ class OpenSegPTv1(nn.Module):
         else:
             yield from self._infer_stream_eager(rooms, depth, dev)
 
+    MAX_GRAPH_SIGNATURES = 4   # captured size signatures kept alive (each holds `depth` private memory pools)
+
     def _infer_stream_graphs(self, rooms, sig, depth, dev):
+        if sig in self._graphs:
+            self._graphs[sig] = self._graphs.pop(sig)          # most recently used last
+        while len(self._graphs) >= self.MAX_GRAPH_SIGNATURES and sig not in self._graphs:
+            self._graphs.pop(next(iter(self._graphs)))         # drop the least recently used signature's graphs
         slots = self._graphs.setdefault(sig, [])
         while len(slots) < min(depth, len(rooms)):
             slots.append(_RoomGraph(self, sig[0], sig[1], dev))
