@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--cpu-sample-points", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--literal", action="store_true", help="reference op sequence (kNN per block, einsum)")
+    ap.add_argument("--linear", default="pob", choices=["pob", "cublas"],
+                    help="frozen linears: pob_linear_forward (fused epilogue) or the cuBLAS route (A/B switch)")
     ap.add_argument("--depth", type=int, default=8,
                     help="rooms whose H2D copy + coordinate-only work run ahead of the feature path (1 = serial)")
     return ap.parse_args()
@@ -122,7 +124,7 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------ CPU port --
 
-def cpu_port_points_per_sec(n_points: int, steps: int, warmup: int, threads: int):
+def cpu_port_points_per_sec(n_points: int, steps: int, warmup: int, threads: int, budget_s: float = 150.0):
     """The reference's op sequence for the same workload on host cores: PTv1 Seg50 (literal path:
     kNN in every block, gather k and v, einsum) over the oracle's brute-force operators + MSP.
     This is the one place bench.py executes oracle/ (cpu_baseline / --impl reference)."""
@@ -150,9 +152,11 @@ def cpu_port_points_per_sec(n_points: int, steps: int, warmup: int, threads: int
                 O.msp_score(logits)
                 if i >= warmup:
                     times.append(time.perf_counter() - t0)
+                    if sum(times) > budget_s:   # bounded: a slow host must not turn K steps into an hour
+                        break
     finally:
         ptv1.pointops = saved
-    return n_points / statistics.median(times), statistics.median(times)
+    return n_points / statistics.median(times), statistics.median(times), len(times)
 
 
 def run_reference_arm(args):
@@ -161,9 +165,9 @@ def run_reference_arm(args):
         return
     cores = os.cpu_count() or 1
     n = args.cpu_sample_points
-    pps, sec = cpu_port_points_per_sec(n, max(1, args.steps), max(0, min(args.warmup, 1)), cores)
+    pps, sec, timed = cpu_port_points_per_sec(n, max(1, args.steps), max(0, min(args.warmup, 1)), cores)
     sample = f"one S3DIS-shaped room of {n} points per step (bounded sample of the 80000-point workload; " \
-             f"brute-force kNN/FPS are O(n^2), so points/s at 80000 would be lower)"
+             f"brute-force kNN/FPS are O(n^2), so points/s at 80000 would be lower); median of {timed} timed steps"
     line = {"impl": "reference", "metric": METRIC, "value": pps, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -248,8 +252,10 @@ def main():
 
     import torch.distributed as dist
     from pointcloudpdf_b200 import _lib, synthetic as S
+    from pointcloudpdf_b200 import ptv1 as _ptv1
     from pointcloudpdf_b200.ptv1 import OpenSegPTv1
     import pointcloudpdf_b200.pointops as pointops
+    _ptv1.set_linear_backend(args.linear)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -392,7 +398,8 @@ def main():
             kernels[name] = {"calls_per_step": d["calls"] / K, "ms_per_step": d["ms"] / K,
                              "share_of_step": d["ms"] / ms_profiled, "alg_MB_per_call": d["alg_bytes"] / d["calls"] / 1e6,
                              "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
-                             "alg_GFLOP_per_call": d["alg_flops"] / d["calls"] / 1e9}
+                             "alg_GFLOP_per_call": d["alg_flops"] / d["calls"] / 1e9,
+                             "achieved_TFLOPs": d["alg_flops"] / d["calls"] / (per_call_ms * 1e-3) / 1e12 if per_call_ms > 0 else 0.0}
         # FPS is the largest kernel by time but it is a serial dependent chain on 16 SMs (latency-bound: no
         # byte or flop roofline describes it; its accounting is reported as `dominant_kernel`).  `roofline`
         # is the largest bandwidth-class kernel of the step: the fused group + aggregate layer.
@@ -401,7 +408,9 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
         except (OSError, ValueError):
             pass
-        bw_class = [k for k in kernels if k not in ("pob_farthest_point_sampling", "pob_knn_grid_query", "pob_knn_grid_build")]
+        # FP32-issue / latency class kernels (their byte roofline says nothing): FPS, kNN, the linears
+        bw_class = [k for k in kernels if k not in ("pob_farthest_point_sampling", "pob_knn_grid_query", "pob_knn_grid_build",
+                                                    "pob_linear_forward")]
         top = bw_class[0] if bw_class else None
         roof = None
         if top:
@@ -438,6 +447,8 @@ def main():
                            "points_per_step_per_gpu": args.points, "classes": NUM_CLASSES, "in_channels": IN_CHANNELS,
                            "op_sequence": "literal (kNN per block, einsum)" if args.literal else
                                           "one kNN per stage + fused aggregation kernel",
+                           "linears": "pob_linear_forward (FP32 FFMA tiles, bias / skip / ReLU on the accumulators)"
+                                      if args.linear == "pob" else "cuBLAS through torch (SIMT sgemm + cuBLASLt bias pass)",
                            "l2": "256 MiB memset between timed iterations (inside the timed region)",
                            "schedule": (f"rooms served in order by OpenSegPTv1.infer_stream, {depth} in flight: each room is one "
                                         f"CUDA-graph replay (coordinate branch: FPS + kNN, forked; feature branch; joined) on "
@@ -456,7 +467,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n = args.cpu_sample_points
-            pps, sec = cpu_port_points_per_sec(n, 1, 1, cores)
+            pps, sec, _ = cpu_port_points_per_sec(n, 3, 1, cores)
             line["cpu_baseline"] = {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"one {n}-point S3DIS-shaped room, reference op sequence over the "
                                               f"brute-force oracle operators, {sec:.2f} s per room (O(n^2): an "

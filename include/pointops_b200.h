@@ -219,6 +219,21 @@ int pob_transition_down_pool(int64_t m, int nsample, int c, const float* z, cons
 int pob_interpolation_add_forward(int64_t n, int c, int k, const float* input, const int* idx, const float* weight,
                                   const float* base, float* output, cudaStream_t stream);
 
+/* FP32 linear layer with fused epilogue (csrc/linear.cu): the eval-mode "Linear + BatchNorm + ReLU",
+ * q/k/v and "Linear + BatchNorm + skip + ReLU" GEMMs of Bottleneck / TransitionDown / TransitionUp
+ * (point_transformer_seg.py:87-95,128-147,178-195), which the reference runs as cuBLAS GEMM + eager
+ * BN / ReLU / add kernels.      out (M, N) = act(A (M, K) @ Wt (K, N) + bias (N) + residual (M, N))
+ * bias / residual may be NULL; relu != 0 applies max(., 0).  lda / ldr / ldo are row strides in floats;
+ * Wt is the weight stored dense K x N (the caller transposes the constant once).  FP32 FFMA, operands are
+ * not rounded to TF32.  Any K, N >= 1 (scalar loads / stores when K, N, strides or pointers are not
+ * 16-byte friendly).  out must not alias A or residual (both are read through the read-only path).
+ * pob_linear_set_config: test / tuning hook, 0 (default) picks the CTA tile from the shape, 1..7 force
+ * 128x32, 64x32 (split-K 2), 32x32 (split-K 4), 16x32 (split-K 8), 64x64, 32x64 (split-K 2),
+ * 16x64 (split-K 4); all 256 threads.                                                                   */
+int pob_linear_set_config(int config);
+int pob_linear_forward(int64_t M, int K, int N, const float* A, int64_t lda, const float* Wt, const float* bias,
+                       const float* residual, int64_t ldr, int relu, float* out, int64_t ldo, cudaStream_t stream);
+
 /* ------------------------------------------------------- grouped vector attention steps --
  * (off the PTv1 path: Point Transformer v2's operators)  Replace the four launchers of
  * src/attention/attention_cuda_kernel.h with the same argument order:

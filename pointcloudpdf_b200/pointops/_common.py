@@ -111,7 +111,11 @@ def const_offset(values: Sequence[int], device) -> torch.Tensor:
     the host->device copy once per distinct value, and the call is legal inside a CUDA-graph capture
     once the value has been seen.  Treat the result as read-only."""
     vals = tuple(int(v) for v in values)
-    k = (vals, device.index if device.index is not None else torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":   # the oracle-backed CPU arm of bench.py drives the same module tree on host tensors
+        k = (vals, device.type)
+    else:
+        k = (vals, device.index if device.index is not None else torch.cuda.current_device())
     t = _CONST_OFFSETS.get(k)
     if t is None:
         if len(_CONST_OFFSETS) > 4096:

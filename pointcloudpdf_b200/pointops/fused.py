@@ -70,6 +70,38 @@ def pt_layer_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, xyz: tor
     return out
 
 
+def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """act(x @ wt + bias + residual): FP32 linear with the epilogue applied on the accumulators
+    (``pob_linear_forward``).  x (M, K) f32 with unit column stride (a column block of a wider tensor is
+    fine), wt (K, N) dense -- the Linear weight transposed once --, bias (N), residual (M, N)."""
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("linear: x must be a CUDA f32 (M, K) tensor with unit column stride")
+    C.require(wt, "wt", torch.float32, 2)
+    m, k = x.shape
+    n = wt.shape[1]
+    if wt.shape[0] != k:
+        raise ValueError(f"linear: x is (M, {k}) but wt is {tuple(wt.shape)}")
+    if bias is not None:
+        C.require(bias, "bias", torch.float32, 1)
+        if bias.shape[0] != n:
+            raise ValueError("linear: bias must be (N,)")
+    ldr = 0
+    if residual is not None:
+        if (not residual.is_cuda or residual.dtype != torch.float32 or residual.shape != (m, n)
+                or residual.stride(1) != 1):
+            raise ValueError("linear: residual must be a CUDA f32 (M, N) tensor with unit column stride")
+        ldr = residual.stride(0)
+    out = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    with _lib.device_guard(x.device):
+        _lib.run("pob_linear_forward", m, k, n, _lib.ptr(x), x.stride(0) if m > 1 else max(x.stride(0), k),
+                 _lib.ptr(wt), _lib.ptr(bias), _lib.ptr(residual), ldr if m > 1 else max(ldr, n), int(bool(relu)),
+                 _lib.ptr(out), n, _lib.current_stream(x.device),
+                 alg_bytes=4 * (m * k + k * n + m * n * (1 + (residual is not None)) + (n if bias is not None else 0)),
+                 alg_flops=2 * m * k * n)
+    return out
+
+
 def affine_act(x: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
                residual: Optional[torch.Tensor] = None, relu: bool = True, inplace: bool = False) -> torch.Tensor:
     """relu?(x * scale + shift + residual) over (rows, c)."""

@@ -23,6 +23,7 @@ which the parity tests compare against.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -103,8 +104,43 @@ def invalidate_frozen(module: nn.Module) -> None:
             m._frozen = None
 
 
-def _linear_act(f, x):  # relu(x @ W'.T + b') in one cublasLt call
-    return torch._addmm_activation(f[1], x, f[0])
+# "pob": every frozen linear runs pob_linear_forward (FP32 FFMA tiles picked from the row count, bias / skip /
+# ReLU applied on the accumulators); "cublas": torch.addmm / _addmm_activation (cuBLAS SIMT GEMM + a cuBLASLt
+# bias pass + pob_affine_act) -- the A/B switch bench.py and the tests use.
+_LINEAR_BACKEND = os.environ.get("POINTOPS_B200_LINEAR", "pob")
+
+
+def set_linear_backend(name: str) -> None:
+    global _LINEAR_BACKEND
+    if name not in ("pob", "cublas"):
+        raise ValueError("linear backend must be 'pob' or 'cublas'")
+    _LINEAR_BACKEND = name
+
+
+_OWN = object()
+
+
+class _Lin:
+    """Frozen linear  y = act(x @ W'.T + b' [+ residual])  with (W', b') from _fold()."""
+    __slots__ = ("w", "wt", "b")
+
+    def __init__(self, W: torch.Tensor, b: Optional[torch.Tensor]):
+        self.w = W.contiguous()             # (N, K); .t() is the view cuBLAS consumes
+        self.wt = self.w.t().contiguous()   # (K, N) dense, what pob_linear_forward streams
+        self.b = b
+
+    def __call__(self, x, relu: bool = False, residual=None, bias=_OWN):
+        b = self.b if bias is _OWN else bias
+        if _LINEAR_BACKEND == "pob":
+            return FZ.linear(x, self.wt, b, residual, relu)
+        wt = self.w.t()
+        if residual is not None:
+            z = torch.addmm(residual, x, wt)
+            return FZ.affine_act(z, None, b, None, relu=relu, inplace=True) if (b is not None or relu) else z
+        if b is None:
+            z = torch.mm(x, wt)
+            return torch.relu_(z) if relu else z
+        return torch._addmm_activation(b, x, wt) if relu else torch.addmm(b, x, wt)
 
 
 class Level:
@@ -232,16 +268,16 @@ class TransitionDown(_Freezable, nn.Module):
     def _freeze(self):
         if self.stride == 1:
             W, b = _fold(self.linear, self.bn)
-            return dict(lin=(W.t(), b))
+            return dict(lin=_Lin(W, b))
         W = self.linear.weight.detach()
         a, sh = _bn_affine(self.bn)
-        return dict(wxyz=_f32(W[:, :3]), wfeat_t=_f32(W[:, 3:]).t(), scale=a.float().contiguous(), shift=sh.float().contiguous())
+        return dict(wxyz=_f32(W[:, :3]), wfeat=_Lin(_f32(W[:, 3:]), None), scale=a.float().contiguous(), shift=sh.float().contiguous())
 
     def forward(self, cloud: Cloud) -> Cloud:
         frozen = self._can_freeze(cloud.x)
         if self.stride == 1:
             if frozen:
-                return cloud.with_feat(_linear_act(self.frozen()["lin"], cloud.x))
+                return cloud.with_feat(self.frozen()["lin"](cloud.x, relu=True))
             return cloud.with_feat(self.relu(self.bn(self.linear(cloud.x))))
         p, x, o = cloud.p, cloud.x, cloud.o
         lvl = cloud.level
@@ -260,7 +296,7 @@ class TransitionDown(_Freezable, nn.Module):
             nxt = None
         if frozen and x.shape[1] % 4 == 0 and self.linear.out_features % 4 == 0:
             f = self.frozen()
-            z = torch.mm(x, f["wfeat_t"])                              # (n, c'): the GEMM on ungathered points
+            z = f["wfeat"](x)                                          # (n, c'): the GEMM on ungathered points
             y = FZ.transition_down_pool(z, p, n_p, cross_idx, f["wxyz"], f["scale"], f["shift"])
             return Cloud(n_p, y, n_o, n_o_host, nxt)
         g = pointops.grouping(cross_idx, x, p, n_p, with_xyz=True)     # (m, ns, 3 + c)
@@ -287,10 +323,10 @@ class TransitionUp(_Freezable, nn.Module):
         W1, b1 = _fold(self.linear1[0], self.linear1[1])
         if isinstance(self.linear2[1], nn.BatchNorm1d):
             W2, b2 = _fold(self.linear2[0], self.linear2[1])
-            return dict(l1=(W1.t(), b1), l2=(W2.t(), b2))
+            return dict(l1=_Lin(W1, b1), l2=_Lin(W2, b2))
         c = W1.shape[0]   # head: linear1 takes cat(x, tiled scene mean); linear2 is Linear + ReLU
         W2, b2 = _fold(self.linear2[0], None)
-        return dict(l1a_t=W1[:, :c].contiguous().t(), l1b_t=W1[:, c:].contiguous().t(), b1=b1, l2=(W2.t(), b2))
+        return dict(l1a=_Lin(W1[:, :c], None), l1b=_Lin(W1[:, c:], b1), l2=_Lin(W2, b2))
 
     def forward(self, fine: Cloud, coarse: Optional[Cloud] = None) -> torch.Tensor:
         frozen = self._can_freeze(fine.x)
@@ -302,9 +338,9 @@ class TransitionUp(_Freezable, nn.Module):
             if b == 1 and frozen:
                 # cat(x, tiled) @ W.T = x @ Wa.T + (mean-feature row) @ Wb.T: the second term is a bias
                 f = self.frozen()
-                t = _linear_act(f["l2"], x.mean(0, keepdim=True))
-                bias = torch.addmm(f["b1"], t, f["l1b_t"]).view(-1)
-                return torch._addmm_activation(bias, x, f["l1a_t"])
+                t = f["l2"](x.mean(0, keepdim=True), relu=True)
+                bias = f["l1b"](t).view(-1)
+                return f["l1a"](x, relu=True, bias=bias)
             if b == 1:
                 mean = x.sum(0, keepdim=True) / sizes[0]
                 tiled = self.linear2(mean).expand(x.shape[0], -1)
@@ -318,8 +354,8 @@ class TransitionUp(_Freezable, nn.Module):
         ahead = lvl is not None and lvl.down is not None and coarse.level is lvl.coarser and coarse.level is not None
         if frozen and fine.x.shape[1] % 4 == 0:
             f = self.frozen()
-            feat = _linear_act(f["l2"], coarse.x)
-            base = _linear_act(f["l1"], fine.x)
+            feat = f["l2"](coarse.x, relu=True)
+            base = f["l1"](fine.x, relu=True)
             if ahead:
                 _wait(lvl.down_ev)
                 up_idx, up_w = lvl.down["up_idx"], lvl.down["up_w"]
@@ -369,8 +405,8 @@ class Bottleneck(_Freezable, nn.Module):
         # every scene has at least nsample points; the caller checks that on the host and else keeps `params`.
         bq, bk, bv = (x.detach().double() for x in (t.linear_q.bias, t.linear_k.bias, t.linear_v.bias))
         W3, b3 = _fold(self.linear3, self.bn3)
-        return dict(l1=(W1.t(), b1), wqkv_t=Wqkv.t(), bqkv=bqkv, params=pack(bw, ob),
-                    params_nobias=pack(bw + aw * (bk - bq), ob + oa * bv), w3_t=W3.t(), b3=b3)
+        return dict(l1=_Lin(W1, b1), qkv=_Lin(Wqkv, bqkv), params=pack(bw, ob),
+                    params_nobias=pack(bw + aw * (bk - bq), ob + oa * bv), l3=_Lin(W3, b3))
 
     def _frozen_ok(self, x) -> bool:
         t = self.transformer
@@ -382,15 +418,14 @@ class Bottleneck(_Freezable, nn.Module):
         if self._frozen_ok(identity):
             f = self.frozen()
             c = self.transformer.out_planes
-            h = _linear_act(f["l1"], identity)
+            h = f["l1"](identity, relu=True)
             if min(C.scene_sizes(cloud.o_host)) >= self.transformer.nsample:   # no placeholder neighbours: biases folded
-                qkv, params = torch.mm(h, f["wqkv_t"]), f["params_nobias"]                    # (n, 3c)
+                qkv, params = f["qkv"](h, bias=None), f["params_nobias"]                      # (n, 3c)
             else:
-                qkv, params = torch.addmm(f["bqkv"], h, f["wqkv_t"]), f["params"]
+                qkv, params = f["qkv"](h), f["params"]
             y = FZ.pt_layer_forward(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], cloud.p, cloud.knn(self.transformer.nsample),
                                     params, out_affine=True)                                  # ... bn2 + relu
-            z = torch.addmm(identity, y, f["w3_t"])                                           # skip + linear3 (bn3 scale folded)
-            return cloud.with_feat(FZ.affine_act(z, None, f["b3"], None, relu=True, inplace=True))
+            return cloud.with_feat(f["l3"](y, relu=True, residual=identity))                  # linear3 + bn3 + skip + ReLU
         x = self.relu(self.bn1(self.linear1(cloud.x)))
         x = self.relu(self.bn2(self.transformer(cloud.with_feat(x))))
         x = self.bn3(self.linear3(x))
@@ -517,13 +552,13 @@ class PointTransformerSeg(_Freezable, nn.Module):
             torch.cuda.current_stream().wait_stream(self._geo_stream)
         if self._can_freeze(d1.x):
             f = self.frozen()
-            return torch.addmm(f["out"][1], _linear_act(f["hid"], d1.x), f["out"][0])
+            return f["out"](f["hid"](d1.x, relu=True))
         return self.cls(d1.x)
 
     def _freeze(self):
         W, b = _fold(self.cls[0], self.cls[1])
         Wo, bo = _fold(self.cls[3], None)
-        return dict(hid=(W.t(), b), out=(Wo.t(), bo))
+        return dict(hid=_Lin(W, b), out=_Lin(Wo, bo))
 
 
 class PointTransformerSeg26(PointTransformerSeg):
@@ -567,13 +602,13 @@ class PTRecognizer(_Freezable, nn.Module):
         r1 = self.dec1(d1, c2.with_feat(r2))
         if self._can_freeze(r1):
             f = self.frozen()
-            return torch.addmm(f["out"][1], _linear_act(f["hid"], r1), f["out"][0])
+            return f["out"](f["hid"](r1, relu=True))
         return self.confidence(r1)
 
     def _freeze(self):
         W, b = _fold(self.confidence[0], self.confidence[1])
         Wo, bo = _fold(self.confidence[3], None)
-        return dict(hid=(W.t(), b), out=(Wo.t(), bo))
+        return dict(hid=_Lin(W, b), out=_Lin(Wo, bo))
 
 
 class _RoomGraph:

@@ -1,0 +1,113 @@
+"""GPU parity of pob_linear_forward (csrc/linear.cu) -- the FP32 linear with fused bias / skip / ReLU
+epilogue that the frozen PTv1 form runs instead of cuBLAS GEMM + eager BN / ReLU / add
+(point_transformer_seg.py:87-95,128-147,178-195) -- against a float64 torch restatement.
+
+Tolerance: 1e-5 relative to the output's magnitude (f32 FFMA accumulation in a different order than
+the reference's cuBLAS GEMM), the bar north_star sets for the floating-point operators."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# the shapes of PTv1-Seg50 on an 80 000-point room (rows shrunk where the tile choice does not depend on them)
+SHAPES = [
+    (20000, 6, 32),      # enc1 input layer: K not a multiple of 4 -> scalar A loads
+    (20000, 32, 13),     # classifier: N not a multiple of 4 -> scalar W loads / stores
+    (17001, 32, 96),     # stage 1 q/k/v, ragged last row tile, tile 128x32
+    (5000, 128, 128),    # tile 64x32, split-K 2
+    (5000, 128, 384),
+    (1250, 256, 768),    # tile 32x32, split-K 4
+    (312, 512, 512),     # tile 16x32, split-K 8
+    (312, 512, 1536),
+    (1, 512, 512),       # the scene-mean row of the decoder head
+    (37, 20, 7),         # nothing aligned
+    (4099, 72, 40),      # K not a multiple of the k-tile, N not a multiple of the column tile
+]
+
+
+def reference(x, wt, bias, residual, relu):
+    y = x.double() @ wt.double()
+    if bias is not None:
+        y = y + bias.double()
+    if residual is not None:
+        y = y + residual.double()
+    return torch.relu(y) if relu else y
+
+
+@pytest.mark.parametrize("m,k,n", SHAPES)
+@pytest.mark.parametrize("epilogue", ["plain", "bias_relu", "bias_residual_relu", "residual"])
+def test_linear_matches_float64(cuda, m, k, n, epilogue):
+    from pointcloudpdf_b200.pointops import fused as FZ
+    g = torch.Generator(device=cuda).manual_seed(m * 31 + k * 7 + n)
+    x = torch.randn(m, k, device=cuda, generator=g)
+    wt = torch.randn(k, n, device=cuda, generator=g) / k ** 0.5
+    bias = torch.randn(n, device=cuda, generator=g) if "bias" in epilogue else None
+    res = torch.randn(m, n, device=cuda, generator=g) if "residual" in epilogue else None
+    relu = "relu" in epilogue
+    out = FZ.linear(x, wt, bias, res, relu)
+    ref = reference(x, wt, bias, res, relu)
+    assert out.shape == (m, n) and out.dtype == torch.float32
+    scale = float(ref.abs().max())
+    assert float((out.double() - ref).abs().max()) <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("config", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("m,k,n", [(700, 64, 96), (130, 6, 13), (33, 512, 64)])
+def test_every_tile_configuration_agrees(cuda, config, m, k, n):
+    """The tile is normally picked from the row count; forced here so that each instantiation
+    (incl. the split-K reductions) sees ragged rows, ragged columns and unaligned shapes."""
+    from pointcloudpdf_b200 import _lib
+    from pointcloudpdf_b200.pointops import fused as FZ
+    g = torch.Generator(device=cuda).manual_seed(config * 1000 + m)
+    x = torch.randn(m, k, device=cuda, generator=g)
+    wt = torch.randn(k, n, device=cuda, generator=g) / k ** 0.5
+    bias = torch.randn(n, device=cuda, generator=g)
+    res = torch.randn(m, n, device=cuda, generator=g)
+    lib = _lib.load()
+    assert lib.pob_linear_set_config(config) == 0
+    try:
+        out = FZ.linear(x, wt, bias, res, True)
+    finally:
+        lib.pob_linear_set_config(0)
+    ref = reference(x, wt, bias, res, True)
+    assert float((out.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_linear_on_column_block_and_rejects_bad_input(cuda):
+    from pointcloudpdf_b200.pointops import fused as FZ
+    g = torch.Generator(device=cuda).manual_seed(5)
+    wide = torch.randn(3000, 96, device=cuda, generator=g)
+    wt = torch.randn(32, 64, device=cuda, generator=g)
+    x = wide[:, 32:64]                                   # row stride 96, unit column stride
+    out = FZ.linear(x, wt, None, None, False)
+    ref = reference(x, wt, None, None, False)
+    assert float((out.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+    with pytest.raises(ValueError):
+        FZ.linear(x.cpu(), wt)                           # no CPU path
+    with pytest.raises(ValueError):
+        FZ.linear(wide, wt)                              # K mismatch
+    with pytest.raises(ValueError):
+        FZ.linear(torch.randn(32, 3000, device=cuda).t(), wt)   # column stride != 1
+
+
+def test_frozen_model_same_logits_on_both_linear_backends(cuda):
+    """OpenSegPTv1 (frozen form) with pob_linear_forward vs the cuBLAS route: same logits to f32
+    summation-order noise, same predictions up to near-ties."""
+    from pointcloudpdf_b200 import ptv1, synthetic as S
+    torch.manual_seed(2024)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        net = ptv1.PointTransformerSeg50(in_channels=6, num_classes=13).to(cuda).eval()
+        b = S.s3dis_batch([9000, 3000], seed=11)
+        data = {k: v.to(cuda) for k, v in b.items() if k in ("coord", "feat", "offset")}
+        outs = {}
+        for backend in ("cublas", "pob"):
+            ptv1.set_linear_backend(backend)
+            with torch.no_grad():
+                outs[backend] = net(data, b["offset"].tolist()).clone()
+    finally:
+        ptv1.set_linear_backend("pob")
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    a, c = outs["pob"], outs["cublas"]
+    assert float((a - c).abs().max()) <= 1e-4 * max(1.0, float(c.abs().max()))
