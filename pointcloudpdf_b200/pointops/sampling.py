@@ -10,6 +10,8 @@ from .. import _lib
 from . import _common as C
 
 USE_GRID = os.environ.get("POINTOPS_B200_FPS_GRID", "1") != "0"
+DIAG_SKIP_FPS = os.environ.get("POINTOPS_B200_DIAG_SKIP_FPS", "0") == "1"   # profiling experiments only
+_DIAG = {}
 
 
 def fps_launch(xyz, offset, new_offset, offset_host, new_offset_host):
@@ -21,6 +23,16 @@ def fps_launch(xyz, offset, new_offset, offset_host, new_offset_host):
     idx = torch.empty((m,), dtype=torch.int32, device=xyz.device)
     if m == 0:
         return idx
+    if DIAG_SKIP_FPS:   # timing diagnostic only (wrong samples): every (n/m)-th point of each scene, no FPS launch
+        parts, s0, m0 = [], 0, 0
+        for e, me in zip(offset_host, new_offset_host):
+            k = me - m0
+            parts.append(s0 + (torch.arange(k, dtype=torch.int64) * (e - s0)) // max(k, 1))
+            s0, m0 = e, me
+        key = (tuple(offset_host), tuple(new_offset_host), str(xyz.device))
+        if key not in _DIAG:
+            _DIAG[key] = torch.cat(parts).to(torch.int32).to(xyz.device)
+        return _DIAG[key]
     tmp = None
     if n_max > 131072:  # beyond the register-resident capacity the kernel streams through tmp
         tmp = torch.empty((xyz.shape[0],), dtype=torch.float32, device=xyz.device)

@@ -39,8 +39,9 @@ from .pointops import fused as FZ
 # ------------------------------------------------------------- frozen (inference) form ----
 # In eval mode under torch.no_grad() every BatchNorm is a per-channel affine map, so the eager glue
 # between the cuBLAS linears folds away:
-#   Linear -> BN -> ReLU                      = one cublasLt GEMM with bias + ReLU epilogue
+#   Linear -> BN -> ReLU                      = one pob_linear_forward (FP32 FFMA GEMM, bias + ReLU on the accumulators)
 #   q, k, v linears                           = one GEMM on concatenated weights
+#   linear3 -> bn3 -> + identity -> ReLU      = one pob_linear_forward with the skip as epilogue operand
 #   gathers, linear_p, relation, linear_w, softmax, aggregation, bn2, ReLU = pob_pt_layer_forward
 #   TransitionDown's Linear(3+C, C') on the grouped tensor = GEMM on the UNGATHERED points (linearity)
 #     + pob_transition_down_pool (gather, coordinate columns, BN, ReLU, max over neighbours)
