@@ -113,6 +113,12 @@ int pob_random_ball_query(int64_t m, int nsample, float min_radius, float max_ra
 /* Diagnostics: device pointer to 2 x uint64 {rounds, samples} that FPS launches accumulate into
  * (mean samples accepted per cluster-wide exchange = samples / rounds), or NULL to switch it off. */
 int pob_fps_set_stats(void* device_u64x2);
+/* Where the chain kernel keeps a scene's points: 0 = registers (5 per point), 1 = shared memory as float4
+ * {x, y, z, idx} with only the running min-distances in registers (capped at 96 registers per thread, so
+ * that other streams' kernels can share the SM with a long chain), -1 (default) = environment
+ * POINTOPS_B200_FPS_POINTS = reg | smem | auto; auto = shared memory from 12 points per thread up.
+ * The sampled indices do not depend on it.                                                          */
+int pob_fps_set_points(int mode);
 int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, const int* offset,
                                 const int* new_offset, float* tmp, int* idx, int cluster_hint,
                                 const void* grid_workspace, int64_t n, float cell_pts, cudaStream_t stream);
@@ -227,9 +233,9 @@ int pob_interpolation_add_forward(int64_t n, int c, int k, const float* input, c
  * Wt is the weight stored dense K x N (the caller transposes the constant once).  FP32 FFMA, operands are
  * not rounded to TF32.  Any K, N >= 1 (scalar loads / stores when K, N, strides or pointers are not
  * 16-byte friendly).  out must not alias A or residual (both are read through the read-only path).
- * pob_linear_set_config: test / tuning hook, 0 (default) picks the CTA tile from the shape, 1..7 force
- * 128x32, 64x32 (split-K 2), 32x32 (split-K 4), 16x32 (split-K 8), 64x64, 32x64 (split-K 2),
- * 16x64 (split-K 4); all 256 threads.                                                                   */
+ * pob_linear_set_config: test / tuning hook, 0 (default) picks the CTA tile from the shape, 1..16 force one of
+ * the instantiated tiles (BM x BN from 16x32 to 256x32 / 128x64, register tiles 4x4, 8x4 or 8x8, intra-CTA
+ * split-K 1..8; csrc/linear.cu lists them).  Only the f32 summation order depends on it.                   */
 int pob_linear_set_config(int config);
 int pob_linear_forward(int64_t M, int K, int N, const float* A, int64_t lda, const float* Wt, const float* bias,
                        const float* residual, int64_t ldr, int relu, float* out, int64_t ldo, cudaStream_t stream);

@@ -282,9 +282,16 @@ __device__ __forceinline__ unsigned long long fps_key(unsigned bits, int idx) {
     return ((unsigned long long)bits << 32) | (unsigned)(~idx);
 }
 
-template <int P, int T>
-__global__ void __launch_bounds__(T, 1)
-fps_chain_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
+//
+// SP (shared-memory points): the coordinates and original indices live ONLY in shared memory, as one float4
+// {x, y, z, idx} per point (one conflict-free LDS.128 per point and sample in the update loops), and the
+// registers keep just the running min-distances.  Same arithmetic, same output; ~90 instead of ~170
+// registers per thread at P = 20, so that on the 16 SMs a stage-1 chain occupies for milliseconds the
+// other rooms' kernels still find room for two of their CTAs instead of one (the chain itself is latency
+// bound and gives up little): measured in profiles/ (bench with and without the chain resident).
+template <int P, int T, bool SP>
+__device__ __forceinline__ void
+fps_chain_body(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
                  const SceneGrid* __restrict__ scenes, const int* __restrict__ cell_start,
                  const float4* __restrict__ sorted, int* __restrict__ idx, unsigned long long* __restrict__ stats) {
     cg::cluster_group cluster = cg::this_cluster();
@@ -300,7 +307,8 @@ fps_chain_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
     const int s_n = scene == 0 ? 0 : offset[scene - 1], e_n = offset[scene];
     const int s_m = scene == 0 ? 0 : new_offset[scene - 1], e_m = new_offset[scene];
 
-    extern __shared__ float s_xyz[];  // [3][T*P]
+    extern __shared__ __align__(16) float s_xyz[];  // SP: float4 {x, y, z, idx}[T*P]; else float [3][T*P]
+    float4* const s_pts = reinterpret_cast<float4*>(s_xyz);
     __shared__ __align__(16) FpsEntry s_warp[2][NG];          // warp entries by round parity (slots >= NW stay zero)
     __shared__ __align__(16) FpsEntry s_msg[2][NG];           // CTA entries from the peers, by round parity
     __shared__ __align__(16) FpsEntry s_sorted[NW][NG];       // per warp: the candidates in key order
@@ -311,36 +319,43 @@ fps_chain_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
     const int total = e_m - s_m;
 
     const bool in_cells = scenes != nullptr && scenes[scene].use_grid;
-    float px[P], py[P], pz[P], pt[P];
-    int pi[P];
+    constexpr int PR = SP ? 1 : P;     // register copies of the points only in the register-resident form
+    float px[PR], py[PR], pz[PR], pt[P];
+    int pi[PR];
     float blo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, bhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     bool box_ok = true;
     const int sbase = in_cells ? __ldg(cell_start + scenes[scene].cell_base) : 0;
 #pragma unroll
     for (int p = 0; p < P; p++) {
         const int pos = in_cells ? ((rank * NW + warp) * P + p) * 32 + lane : p * (C * T) + rank * T + tid;
+        float vx = 0.f, vy = 0.f, vz = 0.f;
+        int vi = INT_MAX;
         if (pos < n) {
             if (in_cells) {
                 const float4 v = __ldg(sorted + sbase + pos);
-                px[p] = v.x; py[p] = v.y; pz[p] = v.z; pi[p] = __float_as_int(v.w);
+                vx = v.x; vy = v.y; vz = v.z; vi = __float_as_int(v.w);
             } else {
                 const int i = s_n + pos;
-                px[p] = __ldg(xyz + (int64_t)i * 3); py[p] = __ldg(xyz + (int64_t)i * 3 + 1); pz[p] = __ldg(xyz + (int64_t)i * 3 + 2);
-                pi[p] = i;
+                vx = __ldg(xyz + (int64_t)i * 3); vy = __ldg(xyz + (int64_t)i * 3 + 1); vz = __ldg(xyz + (int64_t)i * 3 + 2);
+                vi = i;
             }
             pt[p] = PLACEHOLDER_D2;
-            box_ok = box_ok && isfinite(px[p]) && isfinite(py[p]) && isfinite(pz[p]);
-            blo[0] = fminf(blo[0], px[p]); bhi[0] = fmaxf(bhi[0], px[p]);
-            blo[1] = fminf(blo[1], py[p]); bhi[1] = fmaxf(bhi[1], py[p]);
-            blo[2] = fminf(blo[2], pz[p]); bhi[2] = fmaxf(bhi[2], pz[p]);
+            box_ok = box_ok && isfinite(vx) && isfinite(vy) && isfinite(vz);
+            blo[0] = fminf(blo[0], vx); bhi[0] = fmaxf(bhi[0], vx);
+            blo[1] = fminf(blo[1], vy); bhi[1] = fmaxf(bhi[1], vy);
+            blo[2] = fminf(blo[2], vz); bhi[2] = fmaxf(bhi[2], vz);
         } else {
-            px[p] = py[p] = pz[p] = 0.f;
             pt[p] = -1.f;  // never a maximum: fminf keeps it at -1
-            pi[p] = INT_MAX;
         }
         const int slot = (warp * P + p) * 32 + lane;
-        s_xyz[slot] = px[p]; s_xyz[T * P + slot] = py[p]; s_xyz[2 * T * P + slot] = pz[p];
+        if constexpr (SP) {
+            s_pts[slot] = make_float4(vx, vy, vz, __int_as_float(vi));
+        } else {
+            px[p] = vx; py[p] = vy; pz[p] = vz; pi[p] = vi;
+            s_xyz[slot] = vx; s_xyz[T * P + slot] = vy; s_xyz[2 * T * P + slot] = vz;
+        }
     }
+    const float4* const my_pts = s_pts + warp * P * 32 + lane;   // SP: point p of this lane is my_pts[p * 32]
 #pragma unroll
     for (int a = 0; a < 3; a++) {
 #pragma unroll
@@ -421,7 +436,14 @@ fps_chain_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
                 tm &= tm - 1;
                 const float sx = __shfl_sync(FULL, E.x, j), sy = __shfl_sync(FULL, E.y, j), sz = __shfl_sync(FULL, E.z, j);
 #pragma unroll
-                for (int p = 0; p < P; p++) pt[p] = fminf(d2_ref(px[p], py[p], pz[p], sx, sy, sz), pt[p]);
+                for (int p = 0; p < P; p++) {
+                    if constexpr (SP) {
+                        const float4 q = my_pts[p * 32];
+                        pt[p] = fminf(d2_ref(q.x, q.y, q.z, sx, sy, sz), pt[p]);
+                    } else {
+                        pt[p] = fminf(d2_ref(px[p], py[p], pz[p], sx, sy, sz), pt[p]);
+                    }
+                }
             }
         }
         if (emitted >= total) break;  // uniform: `emitted` evolves identically in every thread of the cluster
@@ -434,17 +456,34 @@ fps_chain_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
             wbits = __reduce_max_sync(FULL, __float_as_uint(m));
             int cand = INT_MAX, cp = 0;
 #pragma unroll
-            for (int p = 0; p < P; p++)
-                if (__float_as_uint(pt[p]) == wbits && pi[p] < cand) { cand = pi[p]; cp = p; }
+            for (int p = 0; p < P; p++) {
+                if (__float_as_uint(pt[p]) == wbits) {
+                    int gi;
+                    if constexpr (SP) gi = __float_as_int(my_pts[p * 32].w); else gi = pi[p];
+                    if (gi < cand) { cand = gi; cp = p; }
+                }
+            }
             wi = __reduce_min_sync(FULL, cand);
             const unsigned own = __ballot_sync(FULL, cand == wi && wi != INT_MAX);
             const int ol = own ? __ffs(own) - 1 : 0;
             wslot = __shfl_sync(FULL, (warp * P + cp) * 32 + lane, ol);
             // V_w: this warp's maximum if its own top point became a sample (dry run, nothing stored)
-            tx = s_xyz[wslot]; ty = s_xyz[T * P + wslot]; tz = s_xyz[2 * T * P + wslot];
+            if constexpr (SP) {
+                const float4 t4 = s_pts[wslot];
+                tx = t4.x; ty = t4.y; tz = t4.z;
+            } else {
+                tx = s_xyz[wslot]; ty = s_xyz[T * P + wslot]; tz = s_xyz[2 * T * P + wslot];
+            }
             float vm = 0.f;
 #pragma unroll
-            for (int p = 0; p < P; p++) vm = fmaxf(vm, fminf(d2_ref(px[p], py[p], pz[p], tx, ty, tz), pt[p]));
+            for (int p = 0; p < P; p++) {
+                if constexpr (SP) {
+                    const float4 q = my_pts[p * 32];
+                    vm = fmaxf(vm, fminf(d2_ref(q.x, q.y, q.z, tx, ty, tz), pt[p]));
+                } else {
+                    vm = fmaxf(vm, fminf(d2_ref(px[p], py[p], pz[p], tx, ty, tz), pt[p]));
+                }
+            }
             vbits = __reduce_max_sync(FULL, __float_as_uint(vm));
         }
         const int par = round & 1;
@@ -512,6 +551,22 @@ fps_chain_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
     }
     if (C > 1) cluster.sync();  // nobody leaves while a peer may still be writing into its shared memory
 }
+
+#define POB_FPS_CHAIN_PARAMS                                                                                         \
+    const float *__restrict__ xyz, const int *__restrict__ offset, const int *__restrict__ new_offset,              \
+        const SceneGrid *__restrict__ scenes, const int *__restrict__ cell_start, const float4 *__restrict__ sorted, \
+        int *__restrict__ idx, unsigned long long *__restrict__ stats
+template <int P, int T>
+__global__ void __launch_bounds__(T, 1) fps_chain_kernel(POB_FPS_CHAIN_PARAMS) {
+    fps_chain_body<P, T, false>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats);
+}
+// shared-memory points: capped at 96 registers (24.5 K per 256-thread CTA) so that two 20 K-register CTAs of the
+// fused layer kernel fit next to it on the SM
+template <int P, int T>
+__global__ void __maxnreg__(96) fps_chain_sp_kernel(POB_FPS_CHAIN_PARAMS) {
+    fps_chain_body<P, T, true>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats);
+}
+#undef POB_FPS_CHAIN_PARAMS
 
 // Scenes too large for the register-resident kernels: the same algorithm with the points left in global
 // memory (L2-resident for any realistic scene) and the SAME exact pruning, per tile of 256 points.  A warp
@@ -740,7 +795,14 @@ static int launch_cluster(const void* kernel, int b, int C, int threads, size_t 
 }
 
 template <int T>
-static int launch_chain(int P, int b, int C, cudaStream_t stream, void** args) {
+static int launch_chain(int P, int b, int C, bool smem_points, cudaStream_t stream, void** args) {
+    if (smem_points) {   // points in shared memory (16 bytes each): the long chains, where register pressure costs the neighbours
+#define POB_FPS_CASE(PP) \
+    if (P <= PP) return launch_cluster((const void*)fps_chain_sp_kernel<PP, T>, b, C, T, sizeof(float) * 4 * T * PP, stream, args)
+        POB_FPS_CASE(12); POB_FPS_CASE(16); POB_FPS_CASE(20); POB_FPS_CASE(24); POB_FPS_CASE(32);
+#undef POB_FPS_CASE
+        return POB_ERR_UNSUPPORTED;
+    }
 #define POB_FPS_CASE(PP) \
     if (P <= PP) return launch_cluster((const void*)fps_chain_kernel<PP, T>, b, C, T, sizeof(float) * 3 * T * PP, stream, args)
     POB_FPS_CASE(1); POB_FPS_CASE(2); POB_FPS_CASE(4); POB_FPS_CASE(6); POB_FPS_CASE(8); POB_FPS_CASE(12);
@@ -765,6 +827,12 @@ using namespace pob;
 
 // optional diagnostics buffer (2 x u64 on the device: rounds, samples), set by pob_fps_set_stats
 static unsigned long long* g_fps_stats = nullptr;
+static int g_fps_points = -1;   // -1: environment / default; 0: register-resident points; 1: shared-memory points
+POB_API int pob_fps_set_points(int mode) {
+    if (mode < -1 || mode > 1) return POB_ERR_BAD_ARG;
+    g_fps_points = mode;
+    return 0;
+}
 POB_API int pob_fps_set_stats(void* device_u64x2) { g_fps_stats = (unsigned long long*)device_u64x2; return 0; }
 
 // farthest_point_sampling_cuda_launcher(b, n, xyz, offset, new_offset, tmp, idx)
@@ -826,7 +894,15 @@ POB_API int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, 
         unsigned long long* stats = g_fps_stats;
         void* cargs[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&scenes, (void*)&cell_start,
                          (void*)&sorted, (void*)&idx, (void*)&stats};
-        return launch_chain<T>((int)P, b, C, stream, cargs);
+        // POINTOPS_B200_FPS_POINTS = reg | smem | auto (default): shared-memory points from P = 12 up, where the
+        // register-resident form needs > 128 registers per thread
+        static const int pts_mode = [] {
+            const char* e = getenv("POINTOPS_B200_FPS_POINTS");
+            return !e ? 2 : (strcmp(e, "reg") == 0 ? 0 : (strcmp(e, "smem") == 0 ? 1 : 2));
+        }();
+        const int mode = g_fps_points >= 0 ? g_fps_points : pts_mode;
+        const bool smem_points = mode != 0 && P > 8;
+        return launch_chain<T>((int)P, b, C, smem_points, stream, cargs);
     }
     void* args[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&scenes, (void*)&cell_start,
                     (void*)&sorted, (void*)&idx};

@@ -35,20 +35,22 @@ __device__ __forceinline__ float4 load4(const float* __restrict__ p, int valid) 
     }
 }
 
-template <int BM, int BN, int BK, int KS, bool VEC_K, bool VEC_N>
-__global__ void __launch_bounds__((BM / 4) * (BN / 4) * KS)
+template <int BM, int BN, int BK, int KS, int TM, int TN, bool VEC_K, bool VEC_N>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN) * KS, TM * TN > 16 ? 512 / ((BM / TM) * (BN / TN) * KS) : 0)   // big register tiles: <= 128 registers
 linear_tile_kernel(int64_t M, int K, int N, int col_tiles, const float* __restrict__ A, int64_t lda,
                    const float* __restrict__ Wt, const float* __restrict__ bias, const float* __restrict__ residual,
                    int64_t ldr, int relu, float* __restrict__ out, int64_t ldo) {
-    constexpr int TX = BN / 4, TY = BM / 4, G = TX * TY, NT = G * KS;
+    constexpr int TX = BN / TN, TY = BM / TM, G = TX * TY, NT = G * KS;
+    constexpr int RH = TM / 4, CH = TN / 4;      // a thread's rows / columns come in RH / CH runs of 4, BM/RH (BN/CH) apart
     constexpr int KPG = BK / KS;                 // k-steps of one thread group per k-tile
     constexpr int AS = BM + 4;                   // row stride of As[k][.] (multiple of 4: float4 reads stay aligned)
     constexpr int FA = BM * BK / 4, FB = BK * BN / 4;           // float4s per tile
     constexpr int LA = (FA + NT - 1) / NT, LB = (FB + NT - 1) / NT;
     constexpr int TILE_FLOATS = 2 * BK * (AS + BN);
-    constexpr int RED_FLOATS = KS > 1 ? KS * BM * BN : 0;
+    constexpr int RED_FLOATS = KS > 1 ? (KS / 2) * BM * BN : 0;
     constexpr int SMEM_FLOATS = TILE_FLOATS > RED_FLOATS ? TILE_FLOATS : RED_FLOATS;
-    static_assert(BK % KS == 0 && BM % 4 == 0 && BN % 4 == 0, "tile shape");
+    static_assert(BK % KS == 0 && (TM == 4 || TM == 8) && (TN == 4 || TN == 8) && BM % TM == 0 && BN % TN == 0, "tile shape");
+    static_assert((KS & (KS - 1)) == 0 && SMEM_FLOATS * 4 <= 48 * 1024, "split-K is a power of two; static shared memory");
     __shared__ __align__(16) float smem[SMEM_FLOATS];
     float* As = smem;                            // [2][BK][AS]
     float* Bs = smem + 2 * BK * AS;              // [2][BK][BN]
@@ -104,11 +106,11 @@ linear_tile_kernel(int64_t M, int K, int N, int col_tiles, const float* __restri
         }
     };
 
-    float acc[4][4];
+    float acc[TM][TN];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
     const int tiles = (K + BK - 1) / BK;
     fetch(0);
@@ -121,14 +123,21 @@ linear_tile_kernel(int64_t M, int K, int N, int col_tiles, const float* __restri
         const float* b = Bs + (t & 1) * BK * BN + (g * KPG) * BN + tx * 4;
 #pragma unroll
         for (int kk = 0; kk < KPG; ++kk) {
-            const float4 av = *reinterpret_cast<const float4*>(a + kk * AS);
-            const float4 bv = *reinterpret_cast<const float4*>(b + kk * BN);
-            const float ar[4] = {av.x, av.y, av.z, av.w};
-            const float br[4] = {bv.x, bv.y, bv.z, bv.w};
+            float ar[TM], br[TN];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int h = 0; h < RH; ++h) {
+                const float4 v = *reinterpret_cast<const float4*>(a + kk * AS + h * (BM / RH));
+                ar[h * 4 + 0] = v.x; ar[h * 4 + 1] = v.y; ar[h * 4 + 2] = v.z; ar[h * 4 + 3] = v.w;
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+            for (int h = 0; h < CH; ++h) {
+                const float4 v = *reinterpret_cast<const float4*>(b + kk * BN + h * (BN / CH));
+                br[h * 4 + 0] = v.x; br[h * 4 + 1] = v.y; br[h * 4 + 2] = v.z; br[h * 4 + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
         }
         if (more) stash((t + 1) & 1);            // the other buffer: last read before the previous barrier
         __syncthreads();
@@ -160,50 +169,74 @@ linear_tile_kernel(int64_t M, int K, int N, int col_tiles, const float* __restri
         }
     };
 
-    if (KS == 1) {
+    if (KS > 1) {
+        // split-K: pairwise tree over the thread groups, accumulators exchanged as float4 [quad][thread] (conflict
+        // free); the loop above ended on a barrier, so the tile buffers are free.  Fixed order: deterministic.
+        float4* red = reinterpret_cast<float4*>(smem);
+        constexpr int Q = TM * TN / 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            finish(m0 + ty * 4 + i, n0 + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
-    } else {
-        // the loop ended on a barrier: the tile buffers are free; partial tiles -> red[g][row][col]
-        float* red = smem;
+        for (int half = KS / 2; half >= 1; half >>= 1) {
+            if (g >= half && g < 2 * half) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<float4*>(red + ((g * BM) + ty * 4 + i) * BN + tx * 4) =
-                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        __syncthreads();
-        for (int f = tid; f < BM * BN / 4; f += NT) {
-            const int row = f / (BN / 4), nq = f % (BN / 4);
-            float4 s = *reinterpret_cast<const float4*>(red + row * BN + nq * 4);
+                for (int i = 0; i < TM; ++i)
 #pragma unroll
-            for (int h = 1; h < KS; ++h) {
-                const float4 p = *reinterpret_cast<const float4*>(red + ((h * BM) + row) * BN + nq * 4);
-                s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+                    for (int h = 0; h < CH; ++h)
+                        red[((g - half) * Q + i * CH + h) * G + r] =
+                            make_float4(acc[i][h * 4], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]);
             }
-            finish(m0 + row, n0 + nq * 4, s);
+            __syncthreads();
+            if (g < half) {
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int h = 0; h < CH; ++h) {
+                        const float4 p = red[(g * Q + i * CH + h) * G + r];
+                        acc[i][h * 4] += p.x; acc[i][h * 4 + 1] += p.y; acc[i][h * 4 + 2] += p.z; acc[i][h * 4 + 3] += p.w;
+                    }
+            }
+            if (half > 1) __syncthreads();       // the next round overwrites what this one read
         }
+        if (g != 0) return;
     }
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int h = 0; h < CH; ++h)
+            finish(m0 + (i / 4) * (BM / RH) + ty * 4 + (i % 4), n0 + h * (BN / CH) + tx * 4,
+                   make_float4(acc[i][h * 4], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]));
 }
 
 static inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <int BM, int BN, int BK, int KS>
+template <int BM, int BN, int BK, int KS, int TM, int TN>
 static int launch_linear(int64_t M, int K, int N, const float* A, int64_t lda, const float* Wt, const float* bias,
                          const float* residual, int64_t ldr, int relu, float* out, int64_t ldo, cudaStream_t stream) {
-    const bool vec_k = K % 4 == 0 && lda % 4 == 0 && al16p(A);
-    const bool vec_n = N % 4 == 0 && ldo % 4 == 0 && al16p(Wt) && al16p(out) && al16p(bias) &&
-                       (!residual || (ldr % 4 == 0 && al16p(residual)));
     const int col_tiles = (N + BN - 1) / BN;
     const int64_t row_tiles = (M + BM - 1) / BM;
     const int64_t ctas = row_tiles * col_tiles;
     if (ctas > 0x7fffffffLL) return POB_ERR_UNSUPPORTED;
-    constexpr int NT = (BM / 4) * (BN / 4) * KS;
+    constexpr int NT = (BM / TM) * (BN / TN) * KS;
     const dim3 grid((unsigned)ctas), block(NT);
-#define POB_LINEAR_LAUNCH(VK, VN)                                                                                  \
-    linear_tile_kernel<BM, BN, BK, KS, VK, VN><<<grid, block, 0, stream>>>(M, K, N, col_tiles, A, lda, Wt, bias,    \
-                                                                         residual, ldr, relu, out, ldo)
-    if (vec_k && vec_n) POB_LINEAR_LAUNCH(true, true);
-    else if (vec_k) POB_LINEAR_LAUNCH(true, false);
+    linear_tile_kernel<BM, BN, BK, KS, TM, TN, true, true><<<grid, block, 0, stream>>>(M, K, N, col_tiles, A, lda, Wt, bias,
+                                                                                      residual, ldr, relu, out, ldo);
+    pob_count_launches(1);
+    POB_RETURN_LAST_ERROR();
+}
+
+// shapes that are not 16-byte friendly (the 6-channel input layer, the 13-class head): one tile shape, scalar
+// loads on the unaligned side
+static int launch_linear_unaligned(int64_t M, int K, int N, bool vec_k, bool vec_n, const float* A, int64_t lda,
+                                   const float* Wt, const float* bias, const float* residual, int64_t ldr, int relu,
+                                   float* out, int64_t ldo, cudaStream_t stream) {
+    constexpr int BM = 128, BN = 32;
+    const int col_tiles = (N + BN - 1) / BN;
+    const int64_t ctas = ((M + BM - 1) / BM) * col_tiles;
+    if (ctas > 0x7fffffffLL) return POB_ERR_UNSUPPORTED;
+    const dim3 grid((unsigned)ctas), block(256);
+#define POB_LINEAR_LAUNCH(VK, VN)                                                                                   \
+    linear_tile_kernel<BM, BN, 16, 1, 4, 4, VK, VN><<<grid, block, 0, stream>>>(M, K, N, col_tiles, A, lda, Wt, bias, \
+                                                                              residual, ldr, relu, out, ldo)
+    if (vec_k) POB_LINEAR_LAUNCH(true, false);
     else if (vec_n) POB_LINEAR_LAUNCH(false, true);
     else POB_LINEAR_LAUNCH(false, false);
 #undef POB_LINEAR_LAUNCH
@@ -215,12 +248,24 @@ static int launch_linear(int64_t M, int K, int N, const float* A, int64_t lda, c
 
 using namespace pob;
 
-static int g_linear_force = 0;   // 0 = pick the tile from the shape; 1..7 = force a configuration (tests, tuning)
+static int g_linear_force = 0;   // 0 = pick the tile from the shape; 1..POB_LINEAR_CONFIGS = force one (tests, tuning)
+
+#define POB_LINEAR_CONFIGS 16
 
 POB_API int pob_linear_set_config(int config) {
-    if (config < 0 || config > 7) return POB_ERR_BAD_ARG;
+    if (config < 0 || config > POB_LINEAR_CONFIGS) return POB_ERR_BAD_ARG;
     g_linear_force = config;
     return 0;
+}
+
+// Tile choice.  The shapes are skinny and small (0.16-0.5 GFLOP): what matters is CTAs >= ~2 per SM and as much
+// work per thread as that allows (8 x 8 register tiles where there are rows enough), split-K where there are not.
+static int pick_linear_config(int64_t M, int K, int N) {
+    (void)K;
+    if (M >= 16384) return N <= 32 ? 8 : 10;
+    if (M >= 4096) return N <= 32 ? 2 : 11;
+    if (M >= 1024) return N <= 32 ? 3 : 13;
+    return N <= 32 ? 4 : 13;
 }
 
 // out (M, N) = act(A (M, K) @ Wt (K, N) + bias (N) + residual (M, N)); bias / residual may be NULL; relu != 0
@@ -233,15 +278,31 @@ POB_API int pob_linear_forward(int64_t M, int K, int N, const float* A, int64_t 
     if (M < 0 || K < 1 || N < 1 || lda < K || ldo < N || (residual && ldr < N)) return POB_ERR_BAD_ARG;
     if (M == 0) return 0;
     if (!A || !Wt || !out) return POB_ERR_BAD_ARG;
-    int cfg = g_linear_force;
-    if (cfg == 0) cfg = M >= 16384 ? 1 : M >= 4096 ? 2 : M >= 1024 ? 3 : 4;
+    const bool vec_k = K % 4 == 0 && lda % 4 == 0 && al16p(A);
+    const bool vec_n = N % 4 == 0 && ldo % 4 == 0 && al16p(Wt) && al16p(out) && al16p(bias) &&
+                       (!residual || (ldr % 4 == 0 && al16p(residual)));
+    if (!(vec_k && vec_n))
+        return launch_linear_unaligned(M, K, N, vec_k, vec_n, A, lda, Wt, bias, residual, ldr, relu, out, ldo, stream);
+    const int cfg = g_linear_force ? g_linear_force : pick_linear_config(M, K, N);
+#define POB_LINEAR_CASE(ID, BM, BN, BK, KS, TM, TN) \
+    case ID: return launch_linear<BM, BN, BK, KS, TM, TN>(M, K, N, A, lda, Wt, bias, residual, ldr, relu, out, ldo, stream)
     switch (cfg) {
-        case 1: return launch_linear<128, 32, 16, 1>(M, K, N, A, lda, Wt, bias, residual, ldr, relu, out, ldo, stream);
-        case 2: return launch_linear<64, 32, 16, 2>(M, K, N, A, lda, Wt, bias, residual, ldr, relu, out, ldo, stream);
-        case 3: return launch_linear<32, 32, 32, 4>(M, K, N, A, lda, Wt, bias, residual, ldr, relu, out, ldo, stream);
-        case 4: return launch_linear<16, 32, 32, 8>(M, K, N, A, lda, Wt, bias, residual, ldr, relu, out, ldo, stream);
-        case 5: return launch_linear<64, 64, 16, 1>(M, K, N, A, lda, Wt, bias, residual, ldr, relu, out, ldo, stream);
-        case 6: return launch_linear<32, 64, 32, 2>(M, K, N, A, lda, Wt, bias, residual, ldr, relu, out, ldo, stream);
-        default: return launch_linear<16, 64, 32, 4>(M, K, N, A, lda, Wt, bias, residual, ldr, relu, out, ldo, stream);
+        POB_LINEAR_CASE(1, 128, 32, 16, 1, 4, 4);     // 256 threads
+        POB_LINEAR_CASE(2, 64, 32, 16, 2, 4, 4);
+        POB_LINEAR_CASE(3, 32, 32, 32, 4, 4, 4);
+        POB_LINEAR_CASE(4, 16, 32, 32, 8, 4, 4);
+        POB_LINEAR_CASE(5, 64, 64, 16, 1, 4, 4);
+        POB_LINEAR_CASE(6, 32, 64, 32, 2, 4, 4);
+        POB_LINEAR_CASE(7, 16, 64, 32, 4, 4, 4);
+        POB_LINEAR_CASE(8, 128, 32, 16, 1, 8, 4);     // 128 threads, 8 x 4 register tiles
+        POB_LINEAR_CASE(9, 256, 32, 16, 1, 8, 4);     // 256 threads
+        POB_LINEAR_CASE(10, 128, 64, 16, 1, 8, 8);    // 128 threads, 8 x 8 register tiles
+        POB_LINEAR_CASE(11, 64, 64, 16, 2, 8, 8);     // 128 threads
+        POB_LINEAR_CASE(12, 64, 64, 32, 4, 8, 8);     // 256 threads
+        POB_LINEAR_CASE(13, 32, 64, 32, 8, 8, 8);     // 256 threads
+        POB_LINEAR_CASE(14, 128, 64, 16, 2, 8, 8);    // 256 threads
+        POB_LINEAR_CASE(15, 64, 128, 16, 2, 8, 8);    // 256 threads
+        default: POB_LINEAR_CASE(16, 32, 128, 32, 4, 8, 8);   // 256 threads
     }
+#undef POB_LINEAR_CASE
 }

@@ -65,19 +65,19 @@ for (m, k, n, ep) in SHAPES:
 
     with torch.no_grad():
         rec = dict(shape=[m, k, n], epilogue=ep, cublas_us=timed(cublas, sets))
-        for cfg in range(0, 8):
+        for cfg in range(0, 17):
             lib.pob_linear_set_config(cfg)
             rec[f"pob_cfg{cfg}_us"] = timed(pob, sets)
         lib.pob_linear_set_config(0)
-    best = min(range(1, 8), key=lambda c: rec[f"pob_cfg{c}_us"])
+    best = min(range(1, 17), key=lambda c: rec[f"pob_cfg{c}_us"])
     rec["best_cfg"] = best
     rec["gflop"] = 2 * m * k * n / 1e9
     rec["auto_TFLOPs"] = rec["gflop"] / rec["pob_cfg0_us"] * 1e3
     rows.append(rec)
     print(f"{m:6d} x {k:3d} x {n:4d} {ep:>3}  cublas {rec['cublas_us']:6.1f}  auto {rec['pob_cfg0_us']:6.1f}  " +
-          " ".join(f"c{c}={rec[f'pob_cfg{c}_us']:.1f}" for c in range(1, 8)) + f"  best c{best}", flush=True)
+          " ".join(f"c{c}={rec[f'pob_cfg{c}_us']:.1f}" for c in range(1, 17)) + f"  best c{best}", flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/linear_time.json", "w"), indent=1)
 tot_c = sum(r["cublas_us"] for r in rows); tot_a = sum(r["pob_cfg0_us"] for r in rows)
-tot_b = sum(min(r[f"pob_cfg{c}_us"] for c in range(1, 8)) for r in rows)
+tot_b = sum(min(r[f"pob_cfg{c}_us"] for c in range(1, 17)) for r in rows)
 print(f"sum over shapes: cublas {tot_c:.0f} us, pob auto {tot_a:.0f} us, pob best-per-shape {tot_b:.0f} us")

@@ -141,6 +141,35 @@ def test_fps_full_size_80k_to_20k(cuda, oracle):
     assert torch.equal(out.cpu(), ref)
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("sizes,stride", [([80000], 4), ([52000, 45000], 4), ([100000], 16), ([131072], 64)])
+def test_fps_register_and_shared_memory_points_same_result(cuda, oracle, mode, sizes, stride):
+    """The chain kernel keeps the points either in registers (mode 0) or in shared memory as float4
+    {x, y, z, idx} (mode 1, the default from 12 points per thread up): same arithmetic, same indices.
+    131 072 points = the largest scene the resident kernels take (32 points per thread)."""
+    import pointops
+    from pointcloudpdf_b200 import _lib
+    xyz, offset = make_cloud(sizes, 77 + stride, "room")
+    new_offset = torch.tensor(np.cumsum([max(s // stride, 1) for s in sizes]), dtype=torch.int32)
+    ref = oracle.farthest_point_sampling(xyz, offset, new_offset)
+    lib = _lib.load()
+    assert lib.pob_fps_set_points(mode) == 0
+    try:
+        for with_grid in (True, False):          # cell-ordered + pruning, and the strided layout
+            pointops.clear_caches()
+            if with_grid:
+                out = pointops.farthest_point_sampling(xyz.to(cuda), offset.to(cuda), new_offset.to(cuda))
+            else:
+                out = torch.empty(int(new_offset[-1]), dtype=torch.int32, device=cuda)
+                xyz_d, off_d, noff_d = xyz.to(cuda), offset.to(cuda), new_offset.to(cuda)
+                rc = lib.pob_farthest_point_sampling(len(sizes), max(sizes), _lib.ptr(xyz_d), _lib.ptr(off_d), _lib.ptr(noff_d),
+                                                     None, _lib.ptr(out), 0, None, 0, 0.0, _lib.current_stream(cuda))
+                assert rc == 0
+            assert torch.equal(out.cpu(), ref)
+    finally:
+        lib.pob_fps_set_points(-1)
+
+
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
 def test_fps_every_cluster_size_same_result(cuda, oracle, cluster):
     from pointcloudpdf_b200 import _lib
