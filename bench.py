@@ -55,8 +55,8 @@ def parse():
     ap.add_argument("--cpu-sample-points", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--literal", action="store_true", help="reference op sequence (kNN per block, einsum)")
-    ap.add_argument("--linear", default="pob", choices=["pob", "cublas"],
-                    help="frozen linears: pob_linear_forward (fused epilogue) or the cuBLAS route (A/B switch)")
+    ap.add_argument("--linear", default="auto", choices=["auto", "pob", "cublas"],
+                    help="frozen linears: pob_linear_forward (fused epilogue), the cuBLAS route, or per shape (auto)")
     ap.add_argument("--depth", type=int, default=8,
                     help="rooms whose H2D copy + coordinate-only work run ahead of the feature path (1 = serial)")
     return ap.parse_args()
@@ -447,8 +447,10 @@ def main():
                            "points_per_step_per_gpu": args.points, "classes": NUM_CLASSES, "in_channels": IN_CHANNELS,
                            "op_sequence": "literal (kNN per block, einsum)" if args.literal else
                                           "one kNN per stage + fused aggregation kernel",
-                           "linears": "pob_linear_forward (FP32 FFMA tiles, bias / skip / ReLU on the accumulators)"
-                                      if args.linear == "pob" else "cuBLAS through torch (SIMT sgemm + cuBLASLt bias pass)",
+                           "linears": {"pob": "pob_linear_forward (FP32 FFMA tiles, bias / skip / ReLU on the accumulators)",
+                                       "cublas": "cuBLAS through torch (SIMT sgemm + cuBLASLt bias pass)",
+                                       "auto": "per shape: pob_linear_forward for linears with a bias / skip / ReLU epilogue and the "
+                                               "80000-row layers, cuBLAS for the plain q/k/v GEMMs of the deeper stages"}[args.linear],
                            "l2": "256 MiB memset between timed iterations (inside the timed region)",
                            "schedule": (f"rooms served in order by OpenSegPTv1.infer_stream, {depth} in flight: each room is one "
                                         f"CUDA-graph replay (coordinate branch: FPS + kNN, forked; feature branch; joined) on "

@@ -119,6 +119,9 @@ int pob_fps_set_stats(void* device_u64x2);
  * POINTOPS_B200_FPS_POINTS = reg | smem | auto; auto = shared memory from 12 points per thread up.
  * The sampled indices do not depend on it.                                                          */
 int pob_fps_set_points(int mode);
+/* Diagnostics: cudaOccupancyMaxActiveClusters of the chain kernel for P points per thread in clusters of C CTAs
+ * (smem_points as above) = how many scenes the device can sample concurrently; negative: an error code.     */
+int pob_fps_max_active_clusters(int P, int C, int smem_points);
 int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, const int* offset,
                                 const int* new_offset, float* tmp, int* idx, int cluster_hint,
                                 const void* grid_workspace, int64_t n, float cell_pts, cudaStream_t stream);

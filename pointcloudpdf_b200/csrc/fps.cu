@@ -835,6 +835,38 @@ POB_API int pob_fps_set_points(int mode) {
 }
 POB_API int pob_fps_set_stats(void* device_u64x2) { g_fps_stats = (unsigned long long*)device_u64x2; return 0; }
 
+// Diagnostics: how many clusters of C CTAs of the chain kernel for P points per thread the device can hold at
+// once (cudaOccupancyMaxActiveClusters) -- the ceiling on concurrently sampled scenes.  < 0: error code negated.
+POB_API int pob_fps_max_active_clusters(int P, int C, int smem_points) {
+    constexpr int T = 256;
+    const void* kernel = nullptr;
+    size_t smem = 0;
+#define POB_FPS_PICK(PP)                                                                         \
+    if (!kernel && P <= PP) {                                                                    \
+        kernel = smem_points ? (const void*)fps_chain_sp_kernel<PP, T> : (const void*)fps_chain_kernel<PP, T>; \
+        smem = sizeof(float) * (smem_points ? 4 : 3) * T * PP;                                   \
+    }
+    POB_FPS_PICK(12) POB_FPS_PICK(16) POB_FPS_PICK(20) POB_FPS_PICK(24) POB_FPS_PICK(32)
+#undef POB_FPS_PICK
+    if (!kernel || (C != 1 && C != 2 && C != 4 && C != 8 && C != 16)) return -POB_ERR_BAD_ARG;
+    if (C > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(C * 64));
+    cfg.blockDim = dim3(T);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);
+    return e == cudaSuccess ? n : -(int)e;
+}
+
 // farthest_point_sampling_cuda_launcher(b, n, xyz, offset, new_offset, tmp, idx)
 // (sampling_cuda_kernel.h:13) + the optional kNN grid of the same (xyz, offset) + stream.
 // n_max = largest scene (the reference's `n`); tmp (n floats) is only touched when a scene

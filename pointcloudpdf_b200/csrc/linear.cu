@@ -258,14 +258,17 @@ POB_API int pob_linear_set_config(int config) {
     return 0;
 }
 
-// Tile choice.  The shapes are skinny and small (0.16-0.5 GFLOP): what matters is CTAs >= ~2 per SM and as much
-// work per thread as that allows (8 x 8 register tiles where there are rows enough), split-K where there are not.
+// Tile choice, from the per-shape timings of scratch/linear_time.py on B200 (profiles/): the shapes are skinny
+// and small (0.16-0.5 GFLOP), so a launch is latency bound -- what matters is >= ~2 CTAs per SM with as many
+// warps as possible in flight, split-K where the rows alone do not provide them.  8 x 8 register tiles only
+// pay for the widest outputs.
 static int pick_linear_config(int64_t M, int K, int N) {
     (void)K;
-    if (M >= 16384) return N <= 32 ? 8 : 10;
-    if (M >= 4096) return N <= 32 ? 2 : 11;
-    if (M >= 1024) return N <= 32 ? 3 : 13;
-    return N <= 32 ? 4 : 13;
+    if (M >= 40000) return N <= 32 ? 1 : (N <= 64 ? 5 : 8);
+    if (M >= 10000) return N <= 128 ? 5 : 10;
+    if (M >= 2500) return N <= 256 ? 6 : 10;
+    if (M >= 600) return N <= 512 ? 7 : 11;
+    return N <= 256 ? 7 : (N <= 512 ? 4 : 16);
 }
 
 // out (M, N) = act(A (M, K) @ Wt (K, N) + bias (N) + residual (M, N)); bias / residual may be NULL; relu != 0

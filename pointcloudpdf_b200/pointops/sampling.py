@@ -10,6 +10,7 @@ from .. import _lib
 from . import _common as C
 
 USE_GRID = os.environ.get("POINTOPS_B200_FPS_GRID", "1") != "0"
+CLUSTER_HINT = int(os.environ.get("POINTOPS_B200_FPS_CLUSTER", "0"))   # 0 = the library chooses; 1/2/4/8/16 force
 DIAG_SKIP_FPS = os.environ.get("POINTOPS_B200_DIAG_SKIP_FPS", "0") == "1"   # profiling experiments only
 _DIAG = {}
 
@@ -42,7 +43,7 @@ def fps_launch(xyz, offset, new_offset, offset_host, new_offset_host):
         # TransitionDown) gives the kernel cell-ordered points for exact pruning
         grid = C.get_grid(xyz, offset) if (USE_GRID and n_max > 2048) else None
         _lib.run("pob_farthest_point_sampling", offset.numel(), n_max, _lib.ptr(xyz), _lib.ptr(offset), _lib.ptr(new_offset),
-                 _lib.ptr(tmp), _lib.ptr(idx), 0, _lib.ptr(grid.workspace if grid else None),
+                 _lib.ptr(tmp), _lib.ptr(idx), CLUSTER_HINT, _lib.ptr(grid.workspace if grid else None),
                  xyz.shape[0], grid.cell_pts if grid else 0.0, _lib.current_stream(xyz.device),
                  alg_bytes=12 * xyz.shape[0] + 4 * m, alg_flops=flops)
     return idx

@@ -105,17 +105,29 @@ def invalidate_frozen(module: nn.Module) -> None:
             m._frozen = None
 
 
-# "pob": every frozen linear runs pob_linear_forward (FP32 FFMA tiles picked from the row count, bias / skip /
-# ReLU applied on the accumulators); "cublas": torch.addmm / _addmm_activation (cuBLAS SIMT GEMM + a cuBLASLt
-# bias pass + pob_affine_act) -- the A/B switch bench.py and the tests use.
-_LINEAR_BACKEND = os.environ.get("POINTOPS_B200_LINEAR", "pob")
+# Backend of the frozen linears.  "cublas": torch.addmm / _addmm_activation (cuBLAS SIMT GEMM, a cuBLASLt pass for
+# bias / ReLU, pob_affine_act for the skip); "pob": every linear runs pob_linear_forward (FP32 FFMA tiles, bias /
+# skip / ReLU applied on the accumulators); "auto" (default): pob_linear_forward where it measured faster on B200
+# (scratch/linear_time.py, profiles/): linears WITH an epilogue on >= 600 rows (one launch instead of two), the
+# 80 000-row layers, and shapes that are not 16-byte friendly; cuBLAS for the plain q/k/v GEMMs of the deeper stages.
+_LINEAR_BACKEND = os.environ.get("POINTOPS_B200_LINEAR", "auto")
 
 
 def set_linear_backend(name: str) -> None:
     global _LINEAR_BACKEND
-    if name not in ("pob", "cublas"):
-        raise ValueError("linear backend must be 'pob' or 'cublas'")
+    if name not in ("pob", "cublas", "auto"):
+        raise ValueError("linear backend must be 'pob', 'cublas' or 'auto'")
     _LINEAR_BACKEND = name
+
+
+def _use_pob_linear(m: int, k: int, n: int, epilogue: bool) -> bool:
+    if _LINEAR_BACKEND != "auto":
+        return _LINEAR_BACKEND == "pob"
+    if k % 4 or n % 4:
+        return True
+    if m >= 40000:
+        return n <= 96
+    return epilogue and m >= 600
 
 
 _OWN = object()
@@ -132,7 +144,7 @@ class _Lin:
 
     def __call__(self, x, relu: bool = False, residual=None, bias=_OWN):
         b = self.b if bias is _OWN else bias
-        if _LINEAR_BACKEND == "pob":
+        if _use_pob_linear(x.shape[0], self.wt.shape[0], self.wt.shape[1], b is not None or relu or residual is not None):
             return FZ.linear(x, self.wt, b, residual, relu)
         wt = self.w.t()
         if residual is not None:

@@ -102,12 +102,13 @@ def test_frozen_model_same_logits_on_both_linear_backends(cuda):
         b = S.s3dis_batch([9000, 3000], seed=11)
         data = {k: v.to(cuda) for k, v in b.items() if k in ("coord", "feat", "offset")}
         outs = {}
-        for backend in ("cublas", "pob"):
+        for backend in ("cublas", "pob", "auto"):
             ptv1.set_linear_backend(backend)
             with torch.no_grad():
                 outs[backend] = net(data, b["offset"].tolist()).clone()
     finally:
-        ptv1.set_linear_backend("pob")
+        ptv1.set_linear_backend("auto")
         torch.backends.cuda.matmul.allow_tf32 = prev
-    a, c = outs["pob"], outs["cublas"]
-    assert float((a - c).abs().max()) <= 1e-4 * max(1.0, float(c.abs().max()))
+    c = outs["cublas"]
+    for name in ("pob", "auto"):
+        assert float((outs[name] - c).abs().max()) <= 1e-4 * max(1.0, float(c.abs().max())), name
