@@ -119,6 +119,11 @@ int pob_fps_set_stats(void* device_u64x2);
  * POINTOPS_B200_FPS_POINTS = reg | smem | auto; auto = shared memory from 12 points per thread up.
  * The sampled indices do not depend on it.                                                          */
 int pob_fps_set_points(int mode);
+/* Layout of a chain: 0 = wide (C CTAs of 256 threads, one candidate group per CTA), 1 = tall (C/2 CTAs of 512
+ * threads publishing two groups each: the same 16 groups per exchange on half the SMs; shared-memory points,
+ * up to 24 points per thread), -1 (default) = environment POINTOPS_B200_FPS_LAYOUT = tall | wide (tall).
+ * The sampled indices do not depend on it.                                                          */
+int pob_fps_set_layout(int layout);
 /* Diagnostics: cudaOccupancyMaxActiveClusters of the chain kernel for P points per thread in clusters of C CTAs
  * (smem_points as above) = how many scenes the device can sample concurrently; negative: an error code.     */
 int pob_fps_max_active_clusters(int P, int C, int smem_points);

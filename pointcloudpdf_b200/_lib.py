@@ -33,6 +33,7 @@ SIGNATURES = {
     "pob_random_ball_query": (I, [L, I, F, F, L, I, P, P, P, P, F, P, P, P, P, P]),
     "pob_fps_set_stats": (I, [P]),
     "pob_fps_set_points": (I, [I]),
+    "pob_fps_set_layout": (I, [I]),
     "pob_fps_max_active_clusters": (I, [I, I, I]),
     "pob_farthest_point_sampling": (I, [I, L, P, P, P, P, P, I, P, L, F, P]),
     "pob_grouping_forward": (I, [L, I, I, P, P, P, P]),

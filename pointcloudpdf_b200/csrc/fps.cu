@@ -289,7 +289,12 @@ __device__ __forceinline__ unsigned long long fps_key(unsigned bits, int idx) {
 // registers per thread at P = 20, so that on the 16 SMs a stage-1 chain occupies for milliseconds the
 // other rooms' kernels still find room for two of their CTAs instead of one (the chain itself is latency
 // bound and gives up little): measured in profiles/ (bench with and without the chain resident).
-template <int P, int T, bool SP>
+//
+// GP (groups per CTA, 1 or 2): with GP = 2 a CTA of 16 warps publishes TWO candidates per round (warps 0-7 and
+// 8-15 are independent groups with their own maximum and bound), so a cluster of 8 CTAs x 512 threads ranks the
+// same 16 groups per exchange as 16 CTAs x 256 -- same chain statistics, same per-warp work, half the SMs held
+// for the milliseconds a long chain lasts.
+template <int P, int T, bool SP, int GP>
 __device__ __forceinline__ void
 fps_chain_body(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
                  const SceneGrid* __restrict__ scenes, const int* __restrict__ cell_start,
@@ -301,8 +306,9 @@ fps_chain_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
     const int scene = blockIdx.x / C;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = T / 32;
+    constexpr int WG = NW / GP;          // warps per group
     constexpr int NG = FPS_MAX_CLUSTER;  // group slots ranked per round (unused ones stay zero)
-    static_assert(NW <= NG, "group entries are ranked 16 at a time");
+    static_assert(NW <= NG && NW % GP == 0, "group entries are ranked 16 at a time");
 
     const int s_n = scene == 0 ? 0 : offset[scene - 1], e_n = offset[scene];
     const int s_m = scene == 0 ? 0 : new_offset[scene - 1], e_m = new_offset[scene];
@@ -383,12 +389,12 @@ fps_chain_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
             mbar_init(bar0, 1);
             mbar_init(bar1, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            mbar_expect_tx(bar0, C * (int)sizeof(FpsEntry));
-            mbar_expect_tx(bar1, C * (int)sizeof(FpsEntry));
+            mbar_expect_tx(bar0, C * GP * (int)sizeof(FpsEntry));
+            mbar_expect_tx(bar1, C * GP * (int)sizeof(FpsEntry));
         }
-        if (warp == 0 && lane < C) {  // lane l talks to CTA l
-            rslot0 = mapa_u32(smem_u32(&s_msg[0][rank]), lane);
-            rslot1 = mapa_u32(smem_u32(&s_msg[1][rank]), lane);
+        if (warp % WG == 0 && lane < C) {  // a group's first warp publishes for it: lane l talks to CTA l
+            rslot0 = mapa_u32(smem_u32(&s_msg[0][rank * GP + warp / WG]), lane);
+            rslot1 = mapa_u32(smem_u32(&s_msg[1][rank * GP + warp / WG]), lane);
             rbar0 = mapa_u32(bar0, lane);
             rbar1 = mapa_u32(bar1, lane);
         }
@@ -496,16 +502,16 @@ fps_chain_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
 
         const FpsEntry* src = s_warp[par];
         if (C > 1) {
-            if (warp == 0) {
-                // this CTA's candidate: its best warp entry; V = max(V of that warp, runner-up warp maximum)
-                const FpsEntry e = s_warp[par][lane & (NG - 1)];
-                const unsigned eb = lane < NW ? e.bits : 0u;
-                const int ei = lane < NW ? e.idx : INT_MAX;
+            if (warp % WG == 0) {
+                // this group's candidate: its best warp entry; V = max(V of that warp, runner-up warp maximum)
+                const FpsEntry e = s_warp[par][(warp + lane) & (NG - 1)];   // the group's warps are warp .. warp + WG - 1
+                const unsigned eb = lane < WG ? e.bits : 0u;
+                const int ei = lane < WG ? e.idx : INT_MAX;
                 unsigned cbits; int ci;
                 warp_argmax(eb, ei, cbits, ci);
-                const unsigned whow = __ballot_sync(FULL, lane < NW && eb == cbits && ei == ci);
+                const unsigned whow = __ballot_sync(FULL, lane < WG && eb == cbits && ei == ci);
                 const int wl = whow ? __ffs(whow) - 1 : 0;
-                const unsigned second = __reduce_max_sync(FULL, (lane < NW && lane != wl) ? eb : 0u);
+                const unsigned second = __reduce_max_sync(FULL, (lane < WG && lane != wl) ? eb : 0u);
                 const unsigned vw = __shfl_sync(FULL, e.vbits, wl);
                 const unsigned cv = vw > second ? vw : second;
                 const float cx = __shfl_sync(FULL, e.x, wl), cy = __shfl_sync(FULL, e.y, wl), cz = __shfl_sync(FULL, e.z, wl);
@@ -529,7 +535,7 @@ fps_chain_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
         }
         if (lane < NG) my_sorted[rk] = mine;   // equal keys only among empty slots (same content)
         __syncwarp();
-        if (C > 1 && tid == 0) mbar_expect_tx(par ? bar1 : bar0, C * (int)sizeof(FpsEntry));  // re-arm for round + 2
+        if (C > 1 && tid == 0) mbar_expect_tx(par ? bar1 : bar0, C * GP * (int)sizeof(FpsEntry));  // re-arm for round + 2
         // ---- longest accepted prefix: pair (a < b) needs "a_a leaves a_b untouched" and V_a < tmp[a_b] ----
         bool ok = true;
         if (pb < FPS_KMAX) {
@@ -558,13 +564,19 @@ fps_chain_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
         int *__restrict__ idx, unsigned long long *__restrict__ stats
 template <int P, int T>
 __global__ void __launch_bounds__(T, 1) fps_chain_kernel(POB_FPS_CHAIN_PARAMS) {
-    fps_chain_body<P, T, false>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats);
+    fps_chain_body<P, T, false, 1>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats);
 }
 // shared-memory points: capped at 96 registers (24.5 K per 256-thread CTA) so that two 20 K-register CTAs of the
 // fused layer kernel fit next to it on the SM
 template <int P, int T>
 __global__ void __maxnreg__(96) fps_chain_sp_kernel(POB_FPS_CHAIN_PARAMS) {
-    fps_chain_body<P, T, true>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats);
+    fps_chain_body<P, T, true, 1>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats);
+}
+// "tall" layout: 512 threads, two groups per CTA, points in shared memory (16 bytes x 512 x P <= 227 KB up to
+// P = 24; 128-register cap of a 512-thread CTA)
+template <int P>
+__global__ void __launch_bounds__(512, 1) fps_chain_tall_kernel(POB_FPS_CHAIN_PARAMS) {
+    fps_chain_body<P, 512, true, 2>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats);
 }
 #undef POB_FPS_CHAIN_PARAMS
 
@@ -811,6 +823,15 @@ static int launch_chain(int P, int b, int C, bool smem_points, cudaStream_t stre
     return POB_ERR_UNSUPPORTED;
 }
 
+static int launch_chain_tall(int P, int b, int C, cudaStream_t stream, void** args) {
+#define POB_FPS_CASE(PP) \
+    if (P <= PP) return launch_cluster((const void*)fps_chain_tall_kernel<PP>, b, C, 512, sizeof(float) * 4 * 512 * PP, stream, args)
+    POB_FPS_CASE(2); POB_FPS_CASE(4); POB_FPS_CASE(6); POB_FPS_CASE(8); POB_FPS_CASE(12); POB_FPS_CASE(16);
+    POB_FPS_CASE(20); POB_FPS_CASE(24);
+#undef POB_FPS_CASE
+    return POB_ERR_UNSUPPORTED;
+}
+
 template <int T>
 static int launch_resident(int P, int b, int C, cudaStream_t stream, void** args) {
 #define POB_FPS_CASE(PP) \
@@ -828,6 +849,12 @@ using namespace pob;
 // optional diagnostics buffer (2 x u64 on the device: rounds, samples), set by pob_fps_set_stats
 static unsigned long long* g_fps_stats = nullptr;
 static int g_fps_points = -1;   // -1: environment / default; 0: register-resident points; 1: shared-memory points
+static int g_fps_layout = -1;   // -1: environment / default; 0: wide (C CTAs x 256 threads); 1: tall (C/2 CTAs x 512, two groups each)
+POB_API int pob_fps_set_layout(int layout) {
+    if (layout < -1 || layout > 1) return POB_ERR_BAD_ARG;
+    g_fps_layout = layout;
+    return 0;
+}
 POB_API int pob_fps_set_points(int mode) {
     if (mode < -1 || mode > 1) return POB_ERR_BAD_ARG;
     g_fps_points = mode;
@@ -933,7 +960,16 @@ POB_API int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, 
             return !e ? 2 : (strcmp(e, "reg") == 0 ? 0 : (strcmp(e, "smem") == 0 ? 1 : 2));
         }();
         const int mode = g_fps_points >= 0 ? g_fps_points : pts_mode;
-        const bool smem_points = mode != 0 && P > 8;
+        // POINTOPS_B200_FPS_LAYOUT = tall | wide: tall (default where it applies) samples a scene on C/2 CTAs of 512
+        // threads with two groups each instead of C CTAs of 256 -- the same 16 groups on half the SMs
+        static const int layout_env = [] {
+            const char* e = getenv("POINTOPS_B200_FPS_LAYOUT");
+            return e && strcmp(e, "wide") == 0 ? 0 : 1;
+        }();
+        const int layout = g_fps_layout >= 0 ? g_fps_layout : layout_env;
+        if (layout == 1 && cluster_hint == 0 && C >= 2 && P <= 24 && mode != 0)
+            return launch_chain_tall((int)P, b, C / 2, stream, cargs);
+        const bool smem_points = mode == 1 && P > 8;
         return launch_chain<T>((int)P, b, C, smem_points, stream, cargs);
     }
     void* args[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&scenes, (void*)&cell_start,

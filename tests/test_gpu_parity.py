@@ -141,19 +141,21 @@ def test_fps_full_size_80k_to_20k(cuda, oracle):
     assert torch.equal(out.cpu(), ref)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
-@pytest.mark.parametrize("sizes,stride", [([80000], 4), ([52000, 45000], 4), ([100000], 16), ([131072], 64)])
-def test_fps_register_and_shared_memory_points_same_result(cuda, oracle, mode, sizes, stride):
-    """The chain kernel keeps the points either in registers (mode 0) or in shared memory as float4
-    {x, y, z, idx} (mode 1, the default from 12 points per thread up): same arithmetic, same indices.
-    131 072 points = the largest scene the resident kernels take (32 points per thread)."""
+@pytest.mark.parametrize("points,layout", [(0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("sizes,stride", [([80000], 4), ([52000, 45000], 4), ([100000], 16), ([131072], 64),
+                                          ([20000], 4), ([5000, 3000, 2049], 4)])
+def test_fps_chain_layouts_same_result(cuda, oracle, points, layout, sizes, stride):
+    """The chain kernel keeps the points in registers (points 0) or in shared memory as float4 {x, y, z, idx}
+    (points 1), on C CTAs of 256 threads (layout 0, wide) or on C/2 CTAs of 512 threads publishing two candidate
+    groups each (layout 1, tall; the default): same arithmetic, same indices.  131 072 points = the largest
+    scene the resident kernels take (32 points per thread; tall stops at 24 and hands over to wide)."""
     import pointops
     from pointcloudpdf_b200 import _lib
     xyz, offset = make_cloud(sizes, 77 + stride, "room")
     new_offset = torch.tensor(np.cumsum([max(s // stride, 1) for s in sizes]), dtype=torch.int32)
     ref = oracle.farthest_point_sampling(xyz, offset, new_offset)
     lib = _lib.load()
-    assert lib.pob_fps_set_points(mode) == 0
+    assert lib.pob_fps_set_points(points) == 0 and lib.pob_fps_set_layout(layout) == 0
     try:
         for with_grid in (True, False):          # cell-ordered + pruning, and the strided layout
             pointops.clear_caches()
@@ -168,6 +170,7 @@ def test_fps_register_and_shared_memory_points_same_result(cuda, oracle, mode, s
             assert torch.equal(out.cpu(), ref)
     finally:
         lib.pob_fps_set_points(-1)
+        lib.pob_fps_set_layout(-1)
 
 
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
