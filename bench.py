@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--literal", action="store_true", help="reference op sequence (kNN per block, einsum)")
     ap.add_argument("--linear", default="auto", choices=["auto", "pob", "cublas"],
                     help="frozen linears: pob_linear_forward (fused epilogue), the cuBLAS route, or per shape (auto)")
-    ap.add_argument("--depth", type=int, default=8,
+    ap.add_argument("--depth", type=int, default=12,
                     help="rooms whose H2D copy + coordinate-only work run ahead of the feature path (1 = serial)")
     return ap.parse_args()
 

@@ -130,6 +130,8 @@ def _use_pob_linear(m: int, k: int, n: int, epilogue: bool) -> bool:
     return epilogue and m >= 600
 
 
+GEO_PRIORITY = int(os.environ.get("POINTOPS_B200_GEO_PRIORITY", "0"))
+
 _OWN = object()
 
 
@@ -548,7 +550,10 @@ class PointTransformerSeg(_Freezable, nn.Module):
             level0 = geometry[0]
         elif self.overlap_geometry and p0.is_cuda and self._all_fused:
             if self._geo_stream is None:
-                self._geo_stream = torch.cuda.Stream(device=p0.device)
+                # POINTOPS_B200_GEO_PRIORITY=-1: the coordinate branch (FPS clusters, kNN) on a high-priority stream, so
+                # that a pending 16-CTA cluster is placed ahead of the other rooms' queued CTAs (captured into the room
+                # graphs as the kernel nodes' priority)
+                self._geo_stream = torch.cuda.Stream(device=p0.device, priority=GEO_PRIORITY)
             level0 = self.geometry(p0.contiguous(), o0, offset_host, self._geo_stream)[0]
         c1 = self.enc1(Cloud(p0, x0, o0, offset_host, level0))
         c2 = self.enc2(c1)
