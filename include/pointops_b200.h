@@ -116,12 +116,12 @@ int pob_fps_set_stats(void* device_u64x2);
 /* Where the chain kernel keeps a scene's points: 0 = registers (5 per point), 1 = shared memory as float4
  * {x, y, z, idx} with only the running min-distances in registers (capped at 96 registers per thread, so
  * that other streams' kernels can share the SM with a long chain), -1 (default) = environment
- * POINTOPS_B200_FPS_POINTS = reg | smem | auto; auto = shared memory from 12 points per thread up.
+ * POINTOPS_B200_FPS_POINTS = reg | smem | auto; auto = registers in the wide layout (the tall one is always smem).
  * The sampled indices do not depend on it.                                                          */
 int pob_fps_set_points(int mode);
 /* Layout of a chain: 0 = wide (C CTAs of 256 threads, one candidate group per CTA), 1 = tall (C/2 CTAs of 512
  * threads publishing two groups each: the same 16 groups per exchange on half the SMs; shared-memory points,
- * up to 24 points per thread), -1 (default) = environment POINTOPS_B200_FPS_LAYOUT = tall | wide (tall).
+ * up to 24 points per thread), -1 (default) = environment POINTOPS_B200_FPS_LAYOUT = wide | tall (wide).
  * The sampled indices do not depend on it.                                                          */
 int pob_fps_set_layout(int layout);
 /* Diagnostics: cudaOccupancyMaxActiveClusters of the chain kernel for P points per thread in clusters of C CTAs

@@ -953,18 +953,23 @@ POB_API int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, 
         unsigned long long* stats = g_fps_stats;
         void* cargs[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&scenes, (void*)&cell_start,
                          (void*)&sorted, (void*)&idx, (void*)&stats};
-        // POINTOPS_B200_FPS_POINTS = reg | smem | auto (default): shared-memory points from P = 12 up, where the
-        // register-resident form needs > 128 registers per thread
+        // POINTOPS_B200_FPS_POINTS = reg | smem | auto (default).  wide layout: smem only when asked for (it frees
+        // 76 registers per thread but the LDS per point and sample make the chain 19 % slower, and the bench gains
+        // nothing from the freed registers: profiles/r01d_experiments.md), so auto = reg; the tall layout always
+        // keeps its points in shared memory (a 512-thread CTA has 128 registers per thread).
         static const int pts_mode = [] {
             const char* e = getenv("POINTOPS_B200_FPS_POINTS");
             return !e ? 2 : (strcmp(e, "reg") == 0 ? 0 : (strcmp(e, "smem") == 0 ? 1 : 2));
         }();
         const int mode = g_fps_points >= 0 ? g_fps_points : pts_mode;
-        // POINTOPS_B200_FPS_LAYOUT = tall | wide: tall (default where it applies) samples a scene on C/2 CTAs of 512
-        // threads with two groups each instead of C CTAs of 256 -- the same 16 groups on half the SMs
+        // POINTOPS_B200_FPS_LAYOUT = wide (default) | tall: tall samples a scene on C/2 CTAs of 512 threads with two
+        // groups each instead of C CTAs of 256 -- the same 16 groups on half the SMs, at 1.3-1.5x the time per
+        // sample (16 warps per CTA share the schedulers).  Measured on B200 with 12 rooms in flight: 2.19 ms per
+        // room (tall) against 2.22 (wide), i.e. within noise, while one room alone takes 12.6 ms of FPS instead
+        // of 8.7 -- so wide stays the default (profiles/r01d_experiments.md).
         static const int layout_env = [] {
             const char* e = getenv("POINTOPS_B200_FPS_LAYOUT");
-            return e && strcmp(e, "wide") == 0 ? 0 : 1;
+            return e && strcmp(e, "tall") == 0 ? 1 : 0;
         }();
         const int layout = g_fps_layout >= 0 ? g_fps_layout : layout_env;
         if (layout == 1 && cluster_hint == 0 && C >= 2 && P <= 24 && mode != 0)

@@ -147,7 +147,7 @@ def test_fps_full_size_80k_to_20k(cuda, oracle):
 def test_fps_chain_layouts_same_result(cuda, oracle, points, layout, sizes, stride):
     """The chain kernel keeps the points in registers (points 0) or in shared memory as float4 {x, y, z, idx}
     (points 1), on C CTAs of 256 threads (layout 0, wide) or on C/2 CTAs of 512 threads publishing two candidate
-    groups each (layout 1, tall; the default): same arithmetic, same indices.  131 072 points = the largest
+    groups each (layout 1, tall): same arithmetic, same indices.  131 072 points = the largest
     scene the resident kernels take (32 points per thread; tall stops at 24 and hands over to wide)."""
     import pointops
     from pointcloudpdf_b200 import _lib
