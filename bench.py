@@ -352,7 +352,6 @@ def main():
     barrier()
 
     # ---- value: device-resident inputs, K steps, CUDA events on the main stream ----
-    launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local if rank == 0 else None) as clocks:
         # the sampler's start-up (NVML attach, up to a second) leaves the GPU idle and its clocks parked: a short
@@ -362,6 +361,7 @@ def main():
         else:
             step_resident(0)
         barrier()
+        launches0 = _lib.launch_count()
         e0.record()
         if depth > 1:
             run_stream(resident, K)
