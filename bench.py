@@ -450,6 +450,12 @@ def main():
                     "traffic_source": tr.get("source"), "peak_source": peak_src,
                     "share_of_step": kd["share_of_step"], "avg_launch_ms": kd["ms_per_step"] / kd["calls_per_step"],
                     "alg_bytes_per_launch": kd["alg_MB_per_call"] * 1e6,
+                    "unfused_operator_equivalent": {
+                        "bytes_per_launch": ops[top]["unfused_bytes"] / ops[top]["calls"],
+                        "GBps": ops[top]["unfused_bytes"] / ops[top]["calls"] / (kd["ms_per_step"] / kd["calls_per_step"] * 1e-3) / 1e9,
+                        "what": "SURVEY.md 8(d) algorithmic bytes of the reference operators one launch replaces (knn_query_and_group "
+                                "gather of k with xyz + grouping of v + aggregation forward) / the same launch time: the traffic "
+                                "fusion removed, for context -- NOT bytes this kernel moves"} if ops[top].get("unfused_bytes") else None,
                     "note": "achieved = compulsory bytes of the FUSED op (q, k, v, out rows, indices, coordinates once) / "
                             "mean launch time by CUDA events in the instrumented pass; the (n, ns, C) tensors the unfused "
                             "reference ops would move are never materialised, so the kernel is bound by L2 gathers and FP32 "

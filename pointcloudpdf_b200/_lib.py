@@ -172,14 +172,15 @@ class OpProfile:
     kernels and to compute achieved GB/s from the algorithmic bytes the wrappers report."""
 
     def __init__(self):
-        self.records = []  # (name, start_event, end_event, alg_bytes, alg_flops)
+        self.records = []  # (name, start_event, end_event, alg_bytes, alg_flops, unfused_bytes)
 
     def summary(self):
         import torch
         torch.cuda.synchronize()
         out = {}
-        for name, s, e, nbytes, flops in self.records:
-            d = out.setdefault(name, dict(calls=0, ms=0.0, alg_bytes=0, alg_flops=0))
+        for name, s, e, nbytes, flops, unfused in self.records:
+            d = out.setdefault(name, dict(calls=0, ms=0.0, alg_bytes=0, alg_flops=0, unfused_bytes=0))
+            d["unfused_bytes"] += unfused
             d["calls"] += 1
             d["ms"] += s.elapsed_time(e)
             d["alg_bytes"] += nbytes
@@ -190,7 +191,7 @@ class OpProfile:
 PROFILE = None  # set to an OpProfile() to record
 
 
-def run(name: str, *args, alg_bytes: int = 0, alg_flops: int = 0) -> None:
+def run(name: str, *args, alg_bytes: int = 0, alg_flops: int = 0, unfused_bytes: int = 0) -> None:
     """Call entry point `name`, raise on a non-zero status.  The last positional argument is the
     stream; when profiling, events are recorded on torch's current stream (the same one)."""
     fn = getattr(_lib if _lib is not None else load(), name)
@@ -203,7 +204,7 @@ def run(name: str, *args, alg_bytes: int = 0, alg_flops: int = 0) -> None:
         s.record()
         rc = fn(*args)
         e.record()
-        prof.records.append((name, s, e, int(alg_bytes), int(alg_flops)))
+        prof.records.append((name, s, e, int(alg_bytes), int(alg_flops), int(unfused_bytes)))
     check(rc, name)
 
 

@@ -66,7 +66,11 @@ def pt_layer_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, xyz: tor
                  _lib.ptr(out), c, _lib.current_stream(q.device),
                  # compulsory traffic: q, k, v tables, coordinates, indices, output, once each
                  alg_bytes=4 * (4 * n * c + 3 * n + n * ns) + 4 * params.numel(),
-                 alg_flops=2 * n * ns * (9 + 3 * c + c * wc + wc * wc + 2 * c))
+                 alg_flops=2 * n * ns * (9 + 3 * c + c * wc + wc * wc + 2 * c),
+                 # SURVEY.md 8(d) bytes of the three reference operators this launch stands for: knn_query_and_group
+                 # (k rows with xyz), grouping (v rows), aggregation forward -- the (n, ns, .) tensors they move
+                 unfused_bytes=4 * ((n * c + 6 * n + n * ns + n * ns * (3 + c)) + (n * c + n * ns + n * ns * c)
+                                    + (2 * n * c + n * ns * c + n * ns * wc + n * ns)))
     return out
 
 

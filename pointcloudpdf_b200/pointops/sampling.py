@@ -25,6 +25,10 @@ def fps_launch(xyz, offset, new_offset, offset_host, new_offset_host):
     if m == 0:
         return idx
     if DIAG_SKIP_FPS:   # timing diagnostic only (wrong samples): every (n/m)-th point of each scene, no FPS launch
+        if not _DIAG:
+            import warnings
+            warnings.warn("POINTOPS_B200_DIAG_SKIP_FPS=1: farthest_point_sampling returns a STRIDED sample, not FPS "
+                          "(profiling experiments only)", RuntimeWarning)
         parts, s0, m0 = [], 0, 0
         for e, me in zip(offset_host, new_offset_host):
             k = me - m0
