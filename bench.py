@@ -144,6 +144,72 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class NvmlSampler:
+    """The same samples taken in-process (pynvml, a daemon thread, every 100 ms): NVML is initialised BEFORE the
+    timed region and a poll is two cheap driver queries.  Preferred over the nvidia-smi loop, whose process start-up
+    and per-iteration full queries were seen to stall the launching thread for ~200 ms inside a 0.5 s timed region
+    (profiles/r01d_experiments.md)."""
+    NAMES = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+             ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
+
+    def __init__(self, index):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        handle = None
+        try:   # CUDA ordinal -> NVML handle by UUID (CUDA_VISIBLE_DEVICES may renumber)
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        except Exception:
+            handle = None
+        self.handle = handle if handle is not None else pynvml.nvmlDeviceGetHandleByIndex(index)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        self._poll()                      # fails here, not in the thread, if a query is unsupported
+        self.sm, self.reasons, self.stop = [], set(), threading.Event()
+
+    def _poll(self):
+        nv = self.nv
+        mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        return mhz, mask
+
+    def _loop(self):
+        while not self.stop.is_set():
+            try:
+                mhz, mask = self._poll()
+                self.sm.append(mhz)
+                for name, const in self.NAMES:
+                    if mask & int(getattr(self.nv, const)):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop.set()
+        self.thread.join(timeout=2)
+
+    def summary(self):
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "source": "pynvml"}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": "pynvml"}
+
+
+def make_sampler(index):
+    if index is None:
+        return ClockSampler(None)
+    try:
+        return NvmlSampler(index)
+    except Exception:
+        return ClockSampler(index)      # nvidia-smi loop (B200_PROFILING.md recipe)
+
+
 # ------------------------------------------------------------------------------ CPU port --
 
 def cpu_port_points_per_sec(n_points: int, steps: int, warmup: int, threads: int, budget_s: float = 150.0):
@@ -353,7 +419,7 @@ def main():
 
     # ---- value: device-resident inputs, K steps, CUDA events on the main stream ----
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local if rank == 0 else None) as clocks:
+    with make_sampler(local if rank == 0 else None) as clocks:
         # the sampler's start-up (NVML attach, up to a second) leaves the GPU idle and its clocks parked: a short
         # untimed burst of the same schedule brings them back before the clock starts (W warm-up steps were done above)
         if depth > 1:
