@@ -287,13 +287,15 @@ __device__ __forceinline__ unsigned long long fps_key(unsigned bits, int idx) {
 // {x, y, z, idx} per point (one conflict-free LDS.128 per point and sample in the update loops), and the
 // registers keep just the running min-distances.  Same arithmetic, same output; ~90 instead of ~170
 // registers per thread at P = 20, so that on the 16 SMs a stage-1 chain occupies for milliseconds the
-// other rooms' kernels still find room for two of their CTAs instead of one (the chain itself is latency
-// bound and gives up little): measured in profiles/ (bench with and without the chain resident).
+// other rooms' kernels find room for two of their CTAs instead of one.  Measured (profiles/r01d_experiments.md):
+// the chain alone gets 19 % slower (6.80 -> 8.09 ms at 80 000 points) and the room pipeline gains nothing,
+// so this form is opt-in (POINTOPS_B200_FPS_POINTS=smem) and the base of the tall layout below.
 //
 // GP (groups per CTA, 1 or 2): with GP = 2 a CTA of 16 warps publishes TWO candidates per round (warps 0-7 and
 // 8-15 are independent groups with their own maximum and bound), so a cluster of 8 CTAs x 512 threads ranks the
 // same 16 groups per exchange as 16 CTAs x 256 -- same chain statistics, same per-warp work, half the SMs held
-// for the milliseconds a long chain lasts.
+// for the milliseconds a long chain lasts.  Measured: 10.08 ms instead of 6.80 per 80 000-point scene (16 warps
+// share the schedulers), room pipeline 1.5 % faster at 12 rooms in flight: opt-in (POINTOPS_B200_FPS_LAYOUT=tall).
 template <int P, int T, bool SP, int GP>
 __device__ __forceinline__ void
 fps_chain_body(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
