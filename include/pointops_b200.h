@@ -121,7 +121,9 @@ int pob_fps_set_stats(void* device_u64x2);
 int pob_fps_set_points(int mode);
 /* Layout of a chain: 0 = wide (C CTAs of 256 threads, one candidate group per CTA), 1 = tall (C/2 CTAs of 512
  * threads publishing two groups each: the same 16 groups per exchange on half the SMs; shared-memory points,
- * up to 24 points per thread), -1 (default) = environment POINTOPS_B200_FPS_LAYOUT = wide | tall (wide).
+ * up to 24 points per thread), 2 = fine (EXPERIMENTAL, not yet validated on a GPU: 16 CTAs of 256 threads with
+ * two groups each = 32 groups per exchange), -1 (default) = environment POINTOPS_B200_FPS_LAYOUT = wide | tall |
+ * fine (wide).
  * The sampled indices do not depend on it.                                                          */
 int pob_fps_set_layout(int layout);
 /* Diagnostics: cudaOccupancyMaxActiveClusters of the chain kernel for P points per thread in clusters of C CTAs

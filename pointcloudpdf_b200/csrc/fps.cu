@@ -296,7 +296,12 @@ __device__ __forceinline__ unsigned long long fps_key(unsigned bits, int idx) {
 // same 16 groups per exchange as 16 CTAs x 256 -- same chain statistics, same per-warp work, half the SMs held
 // for the milliseconds a long chain lasts.  Measured: 10.08 ms instead of 6.80 per 80 000-point scene (16 warps
 // share the schedulers), room pipeline 1.5 % faster at 12 rooms in flight: opt-in (POINTOPS_B200_FPS_LAYOUT=tall).
-template <int P, int T, bool SP, int GP>
+//
+// NG (ranking slots, 16 or 32): C x GP candidate groups are ranked per round, one slot per lane at most.  The
+// protocol simulator (scratch/fps_chain_sim.py) accepts 5.6 samples per exchange with 32 groups against 4.4 with
+// 16 (profiles/r01d_fps_chain_sim.txt); the "fine" form (16 CTAs x 256 threads, GP = 2, NG = 32) is built for that
+// and is EXPERIMENTAL: compiled, opt-in (POINTOPS_B200_FPS_LAYOUT=fine), not yet run on a GPU.
+template <int P, int T, bool SP, int GP, int NG = FPS_MAX_CLUSTER>
 __device__ __forceinline__ void
 fps_chain_body(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
                  const SceneGrid* __restrict__ scenes, const int* __restrict__ cell_start,
@@ -309,8 +314,8 @@ fps_chain_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = T / 32;
     constexpr int WG = NW / GP;          // warps per group
-    constexpr int NG = FPS_MAX_CLUSTER;  // group slots ranked per round (unused ones stay zero)
-    static_assert(NW <= NG && NW % GP == 0, "group entries are ranked 16 at a time");
+    // NG group slots are ranked per round (unused ones stay zero)
+    static_assert(NW <= NG && NW % GP == 0 && (NG == 16 || NG == 32), "group entries are ranked 16 or 32 at a time");
 
     const int s_n = scene == 0 ? 0 : offset[scene - 1], e_n = offset[scene];
     const int s_m = scene == 0 ? 0 : new_offset[scene - 1], e_m = new_offset[scene];
@@ -574,6 +579,11 @@ template <int P, int T>
 __global__ void __maxnreg__(96) fps_chain_sp_kernel(POB_FPS_CHAIN_PARAMS) {
     fps_chain_body<P, T, true, 1>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats);
 }
+// "fine" layout (experimental, see NG above): 16 CTAs x 256 threads, two groups per CTA = 32 groups per exchange
+template <int P, int T>
+__global__ void __launch_bounds__(T, 1) fps_chain_fine_kernel(POB_FPS_CHAIN_PARAMS) {
+    fps_chain_body<P, T, false, 2, 32>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats);
+}
 // "tall" layout: 512 threads, two groups per CTA, points in shared memory (16 bytes x 512 x P <= 227 KB up to
 // P = 24; 128-register cap of a 512-thread CTA)
 template <int P>
@@ -825,6 +835,15 @@ static int launch_chain(int P, int b, int C, bool smem_points, cudaStream_t stre
     return POB_ERR_UNSUPPORTED;
 }
 
+template <int T>
+static int launch_chain_fine(int P, int b, int C, cudaStream_t stream, void** args) {
+#define POB_FPS_CASE(PP) \
+    if (P <= PP) return launch_cluster((const void*)fps_chain_fine_kernel<PP, T>, b, C, T, sizeof(float) * 3 * T * PP, stream, args)
+    POB_FPS_CASE(6); POB_FPS_CASE(12); POB_FPS_CASE(20); POB_FPS_CASE(32);
+#undef POB_FPS_CASE
+    return POB_ERR_UNSUPPORTED;
+}
+
 static int launch_chain_tall(int P, int b, int C, cudaStream_t stream, void** args) {
 #define POB_FPS_CASE(PP) \
     if (P <= PP) return launch_cluster((const void*)fps_chain_tall_kernel<PP>, b, C, 512, sizeof(float) * 4 * 512 * PP, stream, args)
@@ -851,9 +870,10 @@ using namespace pob;
 // optional diagnostics buffer (2 x u64 on the device: rounds, samples), set by pob_fps_set_stats
 static unsigned long long* g_fps_stats = nullptr;
 static int g_fps_points = -1;   // -1: environment / default; 0: register-resident points; 1: shared-memory points
-static int g_fps_layout = -1;   // -1: environment / default; 0: wide (C CTAs x 256 threads); 1: tall (C/2 CTAs x 512, two groups each)
+static int g_fps_layout = -1;   // -1: environment / default; 0: wide (C CTAs x 256 threads); 1: tall (C/2 CTAs x 512, two groups
+                                // each); 2: fine (experimental: 16 CTAs x 256, two groups each = 32 groups)
 POB_API int pob_fps_set_layout(int layout) {
-    if (layout < -1 || layout > 1) return POB_ERR_BAD_ARG;
+    if (layout < -1 || layout > 2) return POB_ERR_BAD_ARG;
     g_fps_layout = layout;
     return 0;
 }
@@ -971,11 +991,13 @@ POB_API int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, 
         // of 8.7 -- so wide stays the default (profiles/r01d_experiments.md).
         static const int layout_env = [] {
             const char* e = getenv("POINTOPS_B200_FPS_LAYOUT");
-            return e && strcmp(e, "tall") == 0 ? 1 : 0;
+            return e && strcmp(e, "tall") == 0 ? 1 : (e && strcmp(e, "fine") == 0 ? 2 : 0);
         }();
         const int layout = g_fps_layout >= 0 ? g_fps_layout : layout_env;
         if (layout == 1 && cluster_hint == 0 && C >= 2 && P <= 24 && mode != 0)
             return launch_chain_tall((int)P, b, C / 2, stream, cargs);
+        if (layout == 2 && cluster_hint == 0 && C == 16 && mode != 1)   // experimental: 32 candidate groups
+            return launch_chain_fine<T>((int)P, b, C, stream, cargs);
         const bool smem_points = mode == 1 && P > 8;
         return launch_chain<T>((int)P, b, C, smem_points, stream, cargs);
     }

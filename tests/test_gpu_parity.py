@@ -5,6 +5,8 @@ Bars (BASELINE.json north_star): kNN / FPS indices and grouping bit-exact; aggre
 interpolation and every backward within 1e-5 relative (f32); scores within 1e-6.
 """
 import numpy as np
+import os
+
 import pytest
 import torch
 
@@ -141,7 +143,11 @@ def test_fps_full_size_80k_to_20k(cuda, oracle):
     assert torch.equal(out.cpu(), ref)
 
 
-@pytest.mark.parametrize("points,layout", [(0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("points,layout", [
+    (0, 0), (1, 0), (1, 1),
+    # the 32-group "fine" layout is compiled but has not been run on a GPU yet: POINTOPS_B200_EXPERIMENTAL=1 to try it
+    pytest.param(0, 2, marks=pytest.mark.skipif(os.environ.get("POINTOPS_B200_EXPERIMENTAL") != "1",
+                                                reason="experimental FPS layout (opt-in)"))])
 @pytest.mark.parametrize("sizes,stride", [([80000], 4), ([52000, 45000], 4), ([100000], 16), ([131072], 64),
                                           ([20000], 4), ([5000, 3000, 2049], 4)])
 def test_fps_chain_layouts_same_result(cuda, oracle, points, layout, sizes, stride):
