@@ -11,7 +11,10 @@ for n, m in ((80000, 20000), (20000, 5000), (5000, 1250)):
     xyz = b['coord'].to(dev); off = b['offset'].to(dev); noff = torch.tensor([m], dtype=torch.int32, device=dev)
     grid = C.NeighbourGrid(xyz, off)
     ref = None
-    for name, pts, lay in (("wide/reg", 0, 0), ("wide/smem", 1, 0), ("tall/smem", 1, 1)):
+    forms = [("wide/reg", 0, 0), ("wide/smem", 1, 0), ("tall/smem", 1, 1)]
+    if "--fine" in sys.argv:          # experimental 32-group layout
+        forms.append(("fine/reg", 0, 2))
+    for name, pts, lay in forms:
         lib.pob_fps_set_points(pts); lib.pob_fps_set_layout(lay)
         out = torch.empty(m, dtype=torch.int32, device=dev)
         stats = torch.zeros(2, dtype=torch.int64, device=dev)
