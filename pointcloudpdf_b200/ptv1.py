@@ -146,6 +146,10 @@ class _Lin:
 
     def __call__(self, x, relu: bool = False, residual=None, bias=_OWN):
         b = self.b if bias is _OWN else bias
+        if x.stride(-1) != 1:               # both routes take rows with unit column stride
+            x = x.contiguous()
+        if residual is not None and residual.stride(-1) != 1:
+            residual = residual.contiguous()
         if _use_pob_linear(x.shape[0], self.wt.shape[0], self.wt.shape[1], b is not None or relu or residual is not None):
             return FZ.linear(x, self.wt, b, residual, relu)
         wt = self.w.t()
