@@ -110,28 +110,23 @@ int pob_random_ball_query(int64_t m, int nsample, float min_radius, float max_ra
  * xyz / offset, with its n (rows of xyz) and cell_pts; the kernel then walks the points in cell
  * order and skips, exactly, every warp whose bounding box is out of the new sample's reach.
  * The result is bit-identical with or without it.                                              */
-/* Diagnostics: device pointer to 2 x uint64 {rounds, samples} that FPS launches accumulate into
- * (mean samples accepted per cluster-wide exchange = samples / rounds), or NULL to switch it off. */
-int pob_fps_set_stats(void* device_u64x2);
-/* Where the chain kernel keeps a scene's points: 0 = registers (5 per point), 1 = shared memory as float4
- * {x, y, z, idx} with only the running min-distances in registers (capped at 96 registers per thread, so
- * that other streams' kernels can share the SM with a long chain), -1 (default) = environment
- * POINTOPS_B200_FPS_POINTS = reg | smem | auto; auto = registers in the wide layout (the tall one is always smem).
- * The sampled indices do not depend on it.                                                          */
-int pob_fps_set_points(int mode);
-/* Layout of a chain: 0 = wide (C CTAs of 256 threads, one candidate group per CTA), 1 = tall (C/2 CTAs of 512
- * threads publishing two groups each: the same 16 groups per exchange on half the SMs; shared-memory points,
- * up to 24 points per thread), 2 = fine (EXPERIMENTAL, not yet validated on a GPU: 16 CTAs of 256 threads with
- * two groups each = 32 groups per exchange), -1 (default) = environment POINTOPS_B200_FPS_LAYOUT = wide | tall |
- * fine (wide).
- * The sampled indices do not depend on it.                                                          */
-int pob_fps_set_layout(int layout);
-/* Diagnostics: cudaOccupancyMaxActiveClusters of the chain kernel for P points per thread in clusters of C CTAs
- * (smem_points as above) = how many scenes the device can sample concurrently; negative: an error code.     */
-int pob_fps_max_active_clusters(int P, int C, int smem_points);
+/* variant: which schedule of the same algorithm runs (the sampled indices never depend on it):
+ *   POB_FPS_AUTO   (0) the library chooses (= MERGE)
+ *   POB_FPS_MERGE  (1) merged-list kernel: every warp offers a list of its next local candidates, one cluster
+ *                      exchange accepts the exact global prefix (~20 samples per exchange on room-shaped clouds)
+ *   POB_FPS_CHAIN  (2) round-1 kernel: one candidate + bound per CTA and exchange (~4.5 samples per exchange)
+ *   POB_FPS_SINGLE (3) one sample per exchange
+ * stats_u64x2: NULL, or a device pointer to 2 x uint64 {rounds, samples} the launch accumulates into
+ * (mean samples accepted per cluster-wide exchange = samples / rounds).  Per-call arguments: the library keeps
+ * no tuning state between calls.                                                                          */
+#define POB_FPS_AUTO 0
+#define POB_FPS_MERGE 1
+#define POB_FPS_CHAIN 2
+#define POB_FPS_SINGLE 3
 int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, const int* offset,
                                 const int* new_offset, float* tmp, int* idx, int cluster_hint,
-                                const void* grid_workspace, int64_t n, float cell_pts, cudaStream_t stream);
+                                const void* grid_workspace, int64_t n, float cell_pts, int variant,
+                                void* stats_u64x2, cudaStream_t stream);
 
 /* --------------------------------------------------------- grouping (pointops.grouping2) --
  * grouping_{forward,backward}_cuda_launcher (src/grouping/grouping_cuda_kernel.h:14-15).

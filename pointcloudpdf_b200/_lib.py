@@ -31,11 +31,7 @@ SIGNATURES = {
     "pob_knn_query_bruteforce": (I, [L, I, I, P, P, P, P, P, P, I, P, Z, P]),
     "pob_ball_query": (I, [L, I, F, F, L, I, P, P, P, F, P, P, P, P, P]),
     "pob_random_ball_query": (I, [L, I, F, F, L, I, P, P, P, P, F, P, P, P, P, P]),
-    "pob_fps_set_stats": (I, [P]),
-    "pob_fps_set_points": (I, [I]),
-    "pob_fps_set_layout": (I, [I]),
-    "pob_fps_max_active_clusters": (I, [I, I, I]),
-    "pob_farthest_point_sampling": (I, [I, L, P, P, P, P, P, I, P, L, F, P]),
+    "pob_farthest_point_sampling": (I, [I, L, P, P, P, P, P, I, P, L, F, I, P, P]),
     "pob_grouping_forward": (I, [L, I, I, P, P, P, P]),
     "pob_grouping_backward": (I, [L, I, I, P, P, P, P]),
     "pob_subtraction_forward": (I, [L, I, I, P, P, P, P, P]),

@@ -283,24 +283,10 @@ __device__ __forceinline__ unsigned long long fps_key(unsigned bits, int idx) {
 }
 
 //
-// SP (shared-memory points): the coordinates and original indices live ONLY in shared memory, as one float4
-// {x, y, z, idx} per point (one conflict-free LDS.128 per point and sample in the update loops), and the
-// registers keep just the running min-distances.  Same arithmetic, same output; ~90 instead of ~170
-// registers per thread at P = 20, so that on the 16 SMs a stage-1 chain occupies for milliseconds the
-// other rooms' kernels find room for two of their CTAs instead of one.  Measured (profiles/r01d_experiments.md):
-// the chain alone gets 19 % slower (6.80 -> 8.09 ms at 80 000 points) and the room pipeline gains nothing,
-// so this form is opt-in (POINTOPS_B200_FPS_POINTS=smem) and the base of the tall layout below.
-//
-// GP (groups per CTA, 1 or 2): with GP = 2 a CTA of 16 warps publishes TWO candidates per round (warps 0-7 and
-// 8-15 are independent groups with their own maximum and bound), so a cluster of 8 CTAs x 512 threads ranks the
-// same 16 groups per exchange as 16 CTAs x 256 -- same chain statistics, same per-warp work, half the SMs held
-// for the milliseconds a long chain lasts.  Measured: 10.08 ms instead of 6.80 per 80 000-point scene (16 warps
-// share the schedulers), room pipeline 1.5 % faster at 12 rooms in flight: opt-in (POINTOPS_B200_FPS_LAYOUT=tall).
-//
-// NG (ranking slots, 16 or 32): C x GP candidate groups are ranked per round, one slot per lane at most.  The
-// protocol simulator (scratch/fps_chain_sim.py) accepts 5.6 samples per exchange with 32 groups against 4.4 with
-// 16 (profiles/r01d_fps_chain_sim.txt); the "fine" form (16 CTAs x 256 threads, GP = 2, NG = 32) is built for that
-// and is EXPERIMENTAL: compiled, opt-in (POINTOPS_B200_FPS_LAYOUT=fine), not yet run on a GPU.
+// This is the round-1 kernel, kept as variant 2 (A/B against fps_merge_kernel below, which supersedes it).  The
+// template switches SP (points in shared memory), GP (candidate groups per CTA) and NG (ranking slots) were
+// measured in round 1 (profiles/r01d_experiments.md: none of them moved the room pipeline) and only the
+// register-resident, one-group-per-CTA form <P, T, false, 1, 16> is instantiated.
 template <int P, int T, bool SP, int GP, int NG = FPS_MAX_CLUSTER>
 __device__ __forceinline__ void
 fps_chain_body(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
@@ -573,23 +559,6 @@ template <int P, int T>
 __global__ void __launch_bounds__(T, 1) fps_chain_kernel(POB_FPS_CHAIN_PARAMS) {
     fps_chain_body<P, T, false, 1>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats);
 }
-// shared-memory points: capped at 96 registers (24.5 K per 256-thread CTA) so that two 20 K-register CTAs of the
-// fused layer kernel fit next to it on the SM
-template <int P, int T>
-__global__ void __maxnreg__(96) fps_chain_sp_kernel(POB_FPS_CHAIN_PARAMS) {
-    fps_chain_body<P, T, true, 1>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats);
-}
-// "fine" layout (experimental, see NG above): 16 CTAs x 256 threads, two groups per CTA = 32 groups per exchange
-template <int P, int T>
-__global__ void __launch_bounds__(T, 1) fps_chain_fine_kernel(POB_FPS_CHAIN_PARAMS) {
-    fps_chain_body<P, T, false, 2, 32>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats);
-}
-// "tall" layout: 512 threads, two groups per CTA, points in shared memory (16 bytes x 512 x P <= 227 KB up to
-// P = 24; 128-register cap of a 512-thread CTA)
-template <int P>
-__global__ void __launch_bounds__(512, 1) fps_chain_tall_kernel(POB_FPS_CHAIN_PARAMS) {
-    fps_chain_body<P, 512, true, 2>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats);
-}
 #undef POB_FPS_CHAIN_PARAMS
 
 // Scenes too large for the register-resident kernels: the same algorithm with the points left in global
@@ -798,6 +767,8 @@ fps_stream_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
     cluster.sync();  // nobody leaves while a peer may still be writing into its shared memory
 }
 
+#include "fps_merge.cuh"
+
 static int launch_cluster(const void* kernel, int b, int C, int threads, size_t smem, cudaStream_t stream, void** args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(b * C));
@@ -819,36 +790,11 @@ static int launch_cluster(const void* kernel, int b, int C, int threads, size_t 
 }
 
 template <int T>
-static int launch_chain(int P, int b, int C, bool smem_points, cudaStream_t stream, void** args) {
-    if (smem_points) {   // points in shared memory (16 bytes each): the long chains, where register pressure costs the neighbours
-#define POB_FPS_CASE(PP) \
-    if (P <= PP) return launch_cluster((const void*)fps_chain_sp_kernel<PP, T>, b, C, T, sizeof(float) * 4 * T * PP, stream, args)
-        POB_FPS_CASE(12); POB_FPS_CASE(16); POB_FPS_CASE(20); POB_FPS_CASE(24); POB_FPS_CASE(32);
-#undef POB_FPS_CASE
-        return POB_ERR_UNSUPPORTED;
-    }
+static int launch_chain(int P, int b, int C, cudaStream_t stream, void** args) {
 #define POB_FPS_CASE(PP) \
     if (P <= PP) return launch_cluster((const void*)fps_chain_kernel<PP, T>, b, C, T, sizeof(float) * 3 * T * PP, stream, args)
     POB_FPS_CASE(1); POB_FPS_CASE(2); POB_FPS_CASE(4); POB_FPS_CASE(6); POB_FPS_CASE(8); POB_FPS_CASE(12);
     POB_FPS_CASE(16); POB_FPS_CASE(20); POB_FPS_CASE(24); POB_FPS_CASE(32);
-#undef POB_FPS_CASE
-    return POB_ERR_UNSUPPORTED;
-}
-
-template <int T>
-static int launch_chain_fine(int P, int b, int C, cudaStream_t stream, void** args) {
-#define POB_FPS_CASE(PP) \
-    if (P <= PP) return launch_cluster((const void*)fps_chain_fine_kernel<PP, T>, b, C, T, sizeof(float) * 3 * T * PP, stream, args)
-    POB_FPS_CASE(6); POB_FPS_CASE(12); POB_FPS_CASE(20); POB_FPS_CASE(32);
-#undef POB_FPS_CASE
-    return POB_ERR_UNSUPPORTED;
-}
-
-static int launch_chain_tall(int P, int b, int C, cudaStream_t stream, void** args) {
-#define POB_FPS_CASE(PP) \
-    if (P <= PP) return launch_cluster((const void*)fps_chain_tall_kernel<PP>, b, C, 512, sizeof(float) * 4 * 512 * PP, stream, args)
-    POB_FPS_CASE(2); POB_FPS_CASE(4); POB_FPS_CASE(6); POB_FPS_CASE(8); POB_FPS_CASE(12); POB_FPS_CASE(16);
-    POB_FPS_CASE(20); POB_FPS_CASE(24);
 #undef POB_FPS_CASE
     return POB_ERR_UNSUPPORTED;
 }
@@ -863,70 +809,34 @@ static int launch_resident(int P, int b, int C, cudaStream_t stream, void** args
     return POB_ERR_UNSUPPORTED;
 }
 
+template <int T, int D, int KC>
+static int launch_merge(int P, int b, int C, cudaStream_t stream, void** args) {
+#define POB_FPS_CASE(PP) \
+    if (P <= PP) return launch_cluster((const void*)fps_merge_kernel<PP, T, D, KC>, b, C, T, sizeof(float4) * T * PP, stream, args)
+    POB_FPS_CASE(1); POB_FPS_CASE(2); POB_FPS_CASE(4); POB_FPS_CASE(6); POB_FPS_CASE(8); POB_FPS_CASE(12);
+    POB_FPS_CASE(16); POB_FPS_CASE(20); POB_FPS_CASE(24); POB_FPS_CASE(32);
+#undef POB_FPS_CASE
+    return POB_ERR_UNSUPPORTED;
+}
+
 }  // namespace pob
 
 using namespace pob;
 
-// optional diagnostics buffer (2 x u64 on the device: rounds, samples), set by pob_fps_set_stats
-static unsigned long long* g_fps_stats = nullptr;
-static int g_fps_points = -1;   // -1: environment / default; 0: register-resident points; 1: shared-memory points
-static int g_fps_layout = -1;   // -1: environment / default; 0: wide (C CTAs x 256 threads); 1: tall (C/2 CTAs x 512, two groups
-                                // each); 2: fine (experimental: 16 CTAs x 256, two groups each = 32 groups)
-POB_API int pob_fps_set_layout(int layout) {
-    if (layout < -1 || layout > 2) return POB_ERR_BAD_ARG;
-    g_fps_layout = layout;
-    return 0;
-}
-POB_API int pob_fps_set_points(int mode) {
-    if (mode < -1 || mode > 1) return POB_ERR_BAD_ARG;
-    g_fps_points = mode;
-    return 0;
-}
-POB_API int pob_fps_set_stats(void* device_u64x2) { g_fps_stats = (unsigned long long*)device_u64x2; return 0; }
-
-// Diagnostics: how many clusters of C CTAs of the chain kernel for P points per thread the device can hold at
-// once (cudaOccupancyMaxActiveClusters) -- the ceiling on concurrently sampled scenes.  < 0: error code negated.
-POB_API int pob_fps_max_active_clusters(int P, int C, int smem_points) {
-    constexpr int T = 256;
-    const void* kernel = nullptr;
-    size_t smem = 0;
-#define POB_FPS_PICK(PP)                                                                         \
-    if (!kernel && P <= PP) {                                                                    \
-        kernel = smem_points ? (const void*)fps_chain_sp_kernel<PP, T> : (const void*)fps_chain_kernel<PP, T>; \
-        smem = sizeof(float) * (smem_points ? 4 : 3) * T * PP;                                   \
-    }
-    POB_FPS_PICK(12) POB_FPS_PICK(16) POB_FPS_PICK(20) POB_FPS_PICK(24) POB_FPS_PICK(32)
-#undef POB_FPS_PICK
-    if (!kernel || (C != 1 && C != 2 && C != 4 && C != 8 && C != 16)) return -POB_ERR_BAD_ARG;
-    if (C > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(C * 64));
-    cfg.blockDim = dim3(T);
-    cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)C;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    int n = 0;
-    const cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);
-    return e == cudaSuccess ? n : -(int)e;
-}
-
 // farthest_point_sampling_cuda_launcher(b, n, xyz, offset, new_offset, tmp, idx)
-// (sampling_cuda_kernel.h:13) + the optional kNN grid of the same (xyz, offset) + stream.
+// (sampling_cuda_kernel.h:13) + the optional kNN grid of the same (xyz, offset) + per-call options + stream.
 // n_max = largest scene (the reference's `n`); tmp (n floats) is only touched when a scene
 // exceeds the register-resident capacity (131072 points) and needs no initialisation.
 // grid_workspace: NULL, or the workspace pob_knn_grid_build filled for the same xyz/offset with
 // the same n, b, cell_pts -- enables exact spatial pruning; results are identical either way.
 // cluster_hint: 0 = choose, else force 1/2/4/8/16 CTAs per scene.
+// variant: POB_FPS_AUTO (0) / POB_FPS_MERGE (1) / POB_FPS_CHAIN (2) / POB_FPS_SINGLE (3): same samples, different
+// schedules (A/B and fallback); stats: NULL or 2 x u64 on the device {rounds, samples} accumulated by the launch.
 POB_API int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, const int* offset,
                                         const int* new_offset, float* tmp, int* idx, int cluster_hint,
-                                        const void* grid_workspace, int64_t n, float cell_pts, cudaStream_t stream) {
-    if (b < 1 || n_max < 0 || !offset || !new_offset || !idx) return POB_ERR_BAD_ARG;
+                                        const void* grid_workspace, int64_t n, float cell_pts, int variant,
+                                        void* stats_u64x2, cudaStream_t stream) {
+    if (b < 1 || n_max < 0 || !offset || !new_offset || !idx || variant < 0 || variant > 3) return POB_ERR_BAD_ARG;
     if (n_max == 0) return 0;
     if (!xyz) return POB_ERR_BAD_ARG;
     const SceneGrid* scenes = nullptr;
@@ -941,14 +851,13 @@ POB_API int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, 
         sorted = (const float4*)(ws + L.off_sorted);
     }
     constexpr int T = 256;      // 2 warps per scheduler: the per-iteration overhead scales with warps
-    constexpr int PMAX = 32;    // registers: 5 per point + ~40
+    constexpr int PMAX = 32;    // registers: 5 per point + ~50
     int C = cluster_hint;
     if (C != 1 && C != 2 && C != 4 && C != 8 && C != 16) {
-        static const bool chain_mode = !(getenv("POINTOPS_B200_FPS") && strcmp(getenv("POINTOPS_B200_FPS"), "single") == 0);
-        if (chain_mode) {
-            // a round costs ~1.1-1.5 us whatever C is, and accepts more samples the more groups compete
-            // (measured mean chain 2.2 / 2.9 / 4.0-4.5 at C = 4 / 8 / 16): 16 CTAs unless the scene is tiny
-            // or there are so many scenes that 16-CTA clusters could not all be resident (8 GPCs)
+        if (variant != 3) {
+            // a round costs about the same whatever C is, and accepts more samples the more warps compete:
+            // 16 CTAs unless the scene is tiny or there are so many scenes that 16-CTA clusters could not all
+            // be resident (8 GPCs)
             C = n_max <= 2048 ? 1 : (b <= 8 ? 16 : (b <= 16 ? 8 : 4));
         } else {
             // ~200 ns of cluster exchange per iteration buys a 1/C share of the update work
@@ -969,39 +878,16 @@ POB_API int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, 
                         (void*)&sorted, (void*)&tmp, (void*)&idx, (void*)&tiles_per_warp};
         return launch_cluster((const void*)fps_stream_kernel, b, Cs, FPS_STREAM_THREADS, smem, stream, args);
     }
-    // POINTOPS_B200_FPS=single selects the one-sample-per-exchange kernel (A/B and fallback)
-    static const bool use_chain = !(getenv("POINTOPS_B200_FPS") && strcmp(getenv("POINTOPS_B200_FPS"), "single") == 0);
-    if (use_chain) {
-        unsigned long long* stats = g_fps_stats;
+    if (variant != 3) {
+        unsigned long long* stats = (unsigned long long*)stats_u64x2;
         void* cargs[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&scenes, (void*)&cell_start,
                          (void*)&sorted, (void*)&idx, (void*)&stats};
-        // POINTOPS_B200_FPS_POINTS = reg | smem | auto (default).  wide layout: smem only when asked for (it frees
-        // 76 registers per thread but the LDS per point and sample make the chain 19 % slower, and the bench gains
-        // nothing from the freed registers: profiles/r01d_experiments.md), so auto = reg; the tall layout always
-        // keeps its points in shared memory (a 512-thread CTA has 128 registers per thread).
-        static const int pts_mode = [] {
-            const char* e = getenv("POINTOPS_B200_FPS_POINTS");
-            return !e ? 2 : (strcmp(e, "reg") == 0 ? 0 : (strcmp(e, "smem") == 0 ? 1 : 2));
-        }();
-        const int mode = g_fps_points >= 0 ? g_fps_points : pts_mode;
-        // POINTOPS_B200_FPS_LAYOUT = wide (default) | tall: tall samples a scene on C/2 CTAs of 512 threads with two
-        // groups each instead of C CTAs of 256 -- the same 16 groups on half the SMs, at 1.3-1.5x the time per
-        // sample (16 warps per CTA share the schedulers).  Measured on B200 with 12 rooms in flight: 2.19 ms per
-        // room (tall) against 2.22 (wide), i.e. within noise, while one room alone takes 12.6 ms of FPS instead
-        // of 8.7 -- so wide stays the default (profiles/r01d_experiments.md).
-        static const int layout_env = [] {
-            const char* e = getenv("POINTOPS_B200_FPS_LAYOUT");
-            return e && strcmp(e, "tall") == 0 ? 1 : (e && strcmp(e, "fine") == 0 ? 2 : 0);
-        }();
-        const int layout = g_fps_layout >= 0 ? g_fps_layout : layout_env;
-        if (layout == 1 && cluster_hint == 0 && C >= 2 && P <= 24 && mode != 0)
-            return launch_chain_tall((int)P, b, C / 2, stream, cargs);
-        if (layout == 2 && cluster_hint == 0 && C == 16 && mode != 1)   // experimental: 32 candidate groups
-            return launch_chain_fine<T>((int)P, b, C, stream, cargs);
-        const bool smem_points = mode == 1 && P > 8;
-        return launch_chain<T>((int)P, b, C, smem_points, stream, cargs);
+        if (variant == 2) return launch_chain<T>((int)P, b, C, stream, cargs);
+        return launch_merge<T, 2, 4>((int)P, b, C, stream, cargs);
     }
     void* args[] = {(void*)&xyz, (void*)&offset, (void*)&new_offset, (void*)&scenes, (void*)&cell_start,
                     (void*)&sorted, (void*)&idx};
     return launch_resident<T>((int)P, b, C, stream, args);
 }
+
+

@@ -554,11 +554,9 @@ static int64_t launch_agg_fwd_pipe(int64_t n, int wvec, const float* in, const f
     const size_t smem = (FAST_THREADS / 32) * (pipe::STAGES * stage + 64);
     if (smem > 115000) return 0;  // two CTAs per SM must fit in 227 KB
     auto kern = aggregation_fwd_pipe<L, NS>;
-    static size_t configured = 0;  // per instantiation: the attribute only ever needs to grow
-    if (smem > configured) {
+    {   // the opt-in is per DEVICE and cheap: set it on every launch (a process may drive several GPUs)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { *err = (int)e; return 0; }
-        configured = smem;
     }
     kern<<<(unsigned)ctas, FAST_THREADS, smem, stream>>>(ntiles, wvec, (const float4*)in, (const float4*)pos,
                                                          (const float4*)w, idx, (float4*)out);

@@ -58,7 +58,8 @@ def offset_i32(offset: torch.Tensor, name: str = "offset") -> torch.Tensor:
     if offset.dtype == torch.int32 and offset.is_contiguous():
         return offset
     out = offset.to(torch.int32).contiguous()
-    known = _HOST.get(_key(offset))
+    k = _key(offset)
+    known = _HOST.get(k) if k is not None else None
     if known is not None:
         register_host_offset(out, known[1])
     return out
@@ -75,7 +76,14 @@ _HOST_MAX = 256
 _host_lock = threading.Lock()
 
 
-def _key(t: torch.Tensor) -> Tuple:
+def _key(t: torch.Tensor):
+    """Identity of a tensor's CONTENT as far as torch can tell: storage address + version counter.
+    None = not cacheable: tensors created under torch.inference_mode() carry no version counter, so
+    nothing keyed on them may be reused (the wrappers then recompute, as the reference always does).
+    Writes that bypass the counter (`.data`, DLPack / numpy views, foreign kernels on a raw pointer)
+    are invisible here: call pointops.clear_caches() after such a write."""
+    if t.is_inference():
+        return None
     return (t.data_ptr(), t._version, t.dtype, tuple(t.shape), t.device.index)
 
 
@@ -83,8 +91,11 @@ def register_host_offset(t: torch.Tensor, values: Sequence[int]) -> torch.Tensor
     vals = [int(v) for v in values]
     if len(vals) != t.numel():
         raise ValueError("host values do not match the offset tensor's length")
+    k = _key(t)
+    if k is None:
+        return t
     with _host_lock:
-        _HOST[_key(t)] = (t, vals)  # holding t keeps its storage (and data_ptr) from being recycled
+        _HOST[k] = (t, vals)  # holding t keeps its storage (and data_ptr) from being recycled
         while len(_HOST) > _HOST_MAX:
             _HOST.popitem(last=False)
     return t
@@ -92,6 +103,8 @@ def register_host_offset(t: torch.Tensor, values: Sequence[int]) -> torch.Tensor
 
 def host_offset(t: torch.Tensor) -> List[int]:
     k = _key(t)
+    if k is None:
+        return t.tolist()
     with _host_lock:
         hit = _HOST.get(k)
         if hit is not None:
@@ -119,9 +132,32 @@ def const_offset(values: Sequence[int], device) -> torch.Tensor:
     t = _CONST_OFFSETS.get(k)
     if t is None:
         if len(_CONST_OFFSETS) > 4096:
-            _CONST_OFFSETS.clear()
+            # evict only constants nobody else holds: captured room graphs keep references to the ones
+            # their kernels read (ptv1._RoomGraph.keep), a dropped entry is simply rebuilt on next use
+            import sys
+            for kk in [kk for kk, v in _CONST_OFFSETS.items() if sys.getrefcount(v) <= 3]:
+                del _CONST_OFFSETS[kk]
         t = _CONST_OFFSETS[k] = torch.tensor(vals, dtype=torch.int32).to(device)
+    _CONST_LOG.append(t) if _CONST_LOG is not None else None
     return t
+
+
+_CONST_LOG = None   # while a room graph is being built: every constant handed out (the graph keeps them alive)
+
+
+class record_constants:
+    """Context manager: collect every const_offset() result handed out inside the block."""
+
+    def __enter__(self):
+        global _CONST_LOG
+        self.prev, _CONST_LOG = _CONST_LOG, []
+        self.items = _CONST_LOG
+        return self
+
+    def __exit__(self, *exc):
+        global _CONST_LOG
+        _CONST_LOG = self.prev
+        return False
 
 
 def scene_sizes(vals: Sequence[int]) -> List[int]:
@@ -201,7 +237,10 @@ def get_grid(xyz: torch.Tensor, offset: torch.Tensor) -> NeighbourGrid:
     """Grid for (xyz, offset), reused while both tensors are unchanged (same storage, same
     torch version counter) on the same stream: within one PTv1 stage the same cloud is searched
     by every block, by the next TransitionDown and by the decoder's interpolation."""
-    k = (_key(xyz), _key(offset), _stream_id(xyz.device))
+    kx, ko = _key(xyz), _key(offset)
+    if kx is None or ko is None:      # inference-mode tensors: no version counter, nothing to key on
+        return NeighbourGrid(xyz, offset)
+    k = (kx, ko, _stream_id(xyz.device))
     g = _grids.get(k)
     if g is None:
         g = NeighbourGrid(xyz, offset)
@@ -212,9 +251,13 @@ def get_grid(xyz: torch.Tensor, offset: torch.Tensor) -> NeighbourGrid:
 def cached_knn(nsample: int, xyz, offset, new_xyz, new_offset, want_weight=False):
     """(idx, dist[, weight]) with reuse of identical queries (PTv1 recomputes the same self-kNN
     in every block of a stage, point_transformer_seg.py:51; PTv2 in the same codebase already
-    shares it).  Cached outputs are handed out again only if nobody wrote into them."""
-    k = (int(nsample), bool(want_weight), _key(xyz), _key(offset), _key(new_xyz), _key(new_offset),
-         _stream_id(xyz.device))
+    shares it).  Cached outputs are handed out again only if nobody wrote into them (version counter);
+    the SAME tensor objects go to every caller, so this is for internal callers that treat them as
+    read-only (the PTv1 mirror) -- the public pointops.knn_query returns fresh tensors like the reference."""
+    keys = (_key(xyz), _key(offset), _key(new_xyz), _key(new_offset))
+    if any(kk is None for kk in keys):
+        return get_grid(xyz, offset).query(nsample, new_xyz, new_offset, True, want_weight)
+    k = (int(nsample), bool(want_weight)) + keys + (_stream_id(xyz.device),)
     hit = _knn_results.get(k)
     if hit is not None:
         outs, versions, _keep = hit

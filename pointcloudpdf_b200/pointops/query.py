@@ -28,7 +28,11 @@ class KNNQuery(Function):
         if offset.numel() != new_offset.numel():
             raise ValueError("offset and new_offset must describe the same number of scenes")
         with _lib.device_guard(xyz.device):
+            # fresh tensors per call, like the reference: an identical query (PTv1 repeats its self-kNN in
+            # every block of a stage, point_transformer_seg.py:51) is answered by copying the cached result,
+            # so no two callers ever share storage
             idx, dist, _ = C.cached_knn(nsample, xyz, offset, new_xyz, new_offset)
+            idx, dist = idx.clone(), dist.clone()
         ctx.mark_non_differentiable(idx, dist)
         return idx, dist
 

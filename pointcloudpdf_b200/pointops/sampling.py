@@ -11,35 +11,24 @@ from . import _common as C
 
 USE_GRID = os.environ.get("POINTOPS_B200_FPS_GRID", "1") != "0"
 CLUSTER_HINT = int(os.environ.get("POINTOPS_B200_FPS_CLUSTER", "0"))   # 0 = the library chooses; 1/2/4/8/16 force
-DIAG_SKIP_FPS = os.environ.get("POINTOPS_B200_DIAG_SKIP_FPS", "0") == "1"   # profiling experiments only
-_DIAG = {}
+# schedule of the kernel (include/pointops_b200.h POB_FPS_*): same samples, bit for bit, whatever is chosen
+VARIANTS = {"auto": 0, "merge": 1, "chain": 2, "single": 3}
+VARIANT = VARIANTS[os.environ.get("POINTOPS_B200_FPS", "auto")]
+RESIDENT_MAX = 131072   # points per scene the cluster-resident kernels hold in registers
 
 
-def fps_launch(xyz, offset, new_offset, offset_host, new_offset_host):
+def fps_launch(xyz, offset, new_offset, offset_host, new_offset_host, variant=None, stats=None, cluster_hint=None):
     """The launch itself, for callers that already validated their tensors and know the host copies
-    of both offset vectors (the PTv1 mirror's geometry pass): no checks, no autograd node."""
+    of both offset vectors (the PTv1 mirror's geometry pass): no checks, no autograd node.
+    variant / stats / cluster_hint are per-call (the library keeps no tuning state)."""
     sizes = C.scene_sizes(offset_host)
     m = new_offset_host[-1]
     n_max = max(sizes) if sizes else 0
     idx = torch.empty((m,), dtype=torch.int32, device=xyz.device)
     if m == 0:
         return idx
-    if DIAG_SKIP_FPS:   # timing diagnostic only (wrong samples): every (n/m)-th point of each scene, no FPS launch
-        if not _DIAG:
-            import warnings
-            warnings.warn("POINTOPS_B200_DIAG_SKIP_FPS=1: farthest_point_sampling returns a STRIDED sample, not FPS "
-                          "(profiling experiments only)", RuntimeWarning)
-        parts, s0, m0 = [], 0, 0
-        for e, me in zip(offset_host, new_offset_host):
-            k = me - m0
-            parts.append(s0 + (torch.arange(k, dtype=torch.int64) * (e - s0)) // max(k, 1))
-            s0, m0 = e, me
-        key = (tuple(offset_host), tuple(new_offset_host), str(xyz.device))
-        if key not in _DIAG:
-            _DIAG[key] = torch.cat(parts).to(torch.int32).to(xyz.device)
-        return _DIAG[key]
     tmp = None
-    if n_max > 131072:  # beyond the register-resident capacity the kernel streams through tmp
+    if n_max > RESIDENT_MAX:  # beyond the register-resident capacity the kernel streams through tmp
         tmp = torch.empty((xyz.shape[0],), dtype=torch.float32, device=xyz.device)
     with _lib.device_guard(xyz.device):
         flops = sum(10 * max(mb - 1, 0) * nb for nb, mb in zip(sizes, C.scene_sizes(new_offset_host)))
@@ -47,8 +36,10 @@ def fps_launch(xyz, offset, new_offset, offset_host, new_offset_host):
         # TransitionDown) gives the kernel cell-ordered points for exact pruning
         grid = C.get_grid(xyz, offset) if (USE_GRID and n_max > 2048) else None
         _lib.run("pob_farthest_point_sampling", offset.numel(), n_max, _lib.ptr(xyz), _lib.ptr(offset), _lib.ptr(new_offset),
-                 _lib.ptr(tmp), _lib.ptr(idx), CLUSTER_HINT, _lib.ptr(grid.workspace if grid else None),
-                 xyz.shape[0], grid.cell_pts if grid else 0.0, _lib.current_stream(xyz.device),
+                 _lib.ptr(tmp), _lib.ptr(idx), CLUSTER_HINT if cluster_hint is None else int(cluster_hint),
+                 _lib.ptr(grid.workspace if grid else None), xyz.shape[0], grid.cell_pts if grid else 0.0,
+                 VARIANT if variant is None else VARIANTS[variant] if isinstance(variant, str) else int(variant),
+                 _lib.ptr(stats), _lib.current_stream(xyz.device),
                  alg_bytes=12 * xyz.shape[0] + 4 * m, alg_flops=flops)
     return idx
 

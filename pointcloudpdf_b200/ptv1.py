@@ -70,21 +70,35 @@ def _f32(t):
     return t.detach().float().contiguous()
 
 
+_GENERATION = [0]   # bumped whenever folded weights are dropped or a backend switch changes what a forward launches
+
+
+def _bump_generation() -> None:
+    """Captured room graphs hold raw pointers to the folded tensors and a fixed kernel sequence: anything
+    that frees / rebuilds those tensors or changes the sequence makes every captured graph stale."""
+    _GENERATION[0] += 1
+
+
 class _Freezable:
     """Mixin: cache of folded inference tensors, dropped whenever the parameters may have changed."""
     _frozen = None
     use_frozen = True
 
+    def _drop_frozen(self):
+        if self._frozen is not None:
+            self._frozen = None
+        _bump_generation()
+
     def train(self, mode: bool = True):
-        self._frozen = None
+        self._drop_frozen()
         return super().train(mode)
 
     def _apply(self, fn, *args, **kwargs):
-        self._frozen = None
+        self._drop_frozen()
         return super()._apply(fn, *args, **kwargs)
 
     def _load_from_state_dict(self, *args, **kwargs):
-        self._frozen = None
+        self._drop_frozen()
         return super()._load_from_state_dict(*args, **kwargs)
 
     def _can_freeze(self, x: torch.Tensor) -> bool:
@@ -100,9 +114,11 @@ class _Freezable:
 
 
 def invalidate_frozen(module: nn.Module) -> None:
+    """Call after editing weights in place: drops the folded tensors (and with them every captured room graph)."""
     for m in module.modules():
         if isinstance(m, _Freezable):
             m._frozen = None
+    _bump_generation()
 
 
 # Backend of the frozen linears.  "cublas": torch.addmm / _addmm_activation (cuBLAS SIMT GEMM, a cuBLASLt pass for
@@ -117,6 +133,8 @@ def set_linear_backend(name: str) -> None:
     global _LINEAR_BACKEND
     if name not in ("pob", "cublas", "auto"):
         raise ValueError("linear backend must be 'pob', 'cublas' or 'auto'")
+    if name != _LINEAR_BACKEND:
+        _bump_generation()
     _LINEAR_BACKEND = name
 
 
@@ -494,6 +512,7 @@ class PointTransformerSeg(_Freezable, nn.Module):
             if isinstance(m, _Freezable):
                 m.use_frozen = bool(fused)
         self._all_fused = bool(fused)
+        _bump_generation()
         return self
 
     @torch.no_grad()
@@ -641,6 +660,7 @@ class _RoomGraph:
     def __init__(self, model: "OpenSegPTv1", offset_host, in_channels: int, device):
         self.offset_host = [int(v) for v in offset_host]
         n = self.offset_host[-1]
+        self.method = model.method
         self.stream = torch.cuda.Stream(device=device)
         self.coord = torch.empty((n, 3), dtype=torch.float32, device=device)
         self.feat = torch.empty((n, in_channels), dtype=torch.float32, device=device)
@@ -649,21 +669,27 @@ class _RoomGraph:
         self.feat.zero_()
         d = dict(coord=self.coord, feat=self.feat, offset=self.offset)
         torch.cuda.synchronize(device)
-        with torch.cuda.stream(self.stream):
-            # eager dry run: folds the BatchNorms, creates the constant offset tensors, the geometry
-            # stream, cuBLAS handles / workspaces -- nothing lazy may be left for the capture
-            model.forward(d, self.offset_host)
-        torch.cuda.synchronize(device)
-        pointops.clear_caches()      # the capture must launch every kernel itself
-        self.graph = torch.cuda.CUDAGraph()
-        before = _lib.launch_count()
-        # thread_local: other threads of the process (NCCL watchdog, data loaders) may keep calling CUDA
-        with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode="thread_local"):
-            out = model.forward(d, self.offset_host)
+        with C.record_constants() as consts:
+            with torch.cuda.stream(self.stream):
+                # eager dry run: folds the BatchNorms, creates the constant offset tensors, the geometry
+                # stream, cuBLAS handles / workspaces -- nothing lazy may be left for the capture
+                model.forward(d, self.offset_host)
+            torch.cuda.synchronize(device)
+            pointops.clear_caches()      # the capture must launch every kernel itself
+            self.graph = torch.cuda.CUDAGraph()
+            before = _lib.launch_count()
+            # thread_local: other threads of the process (NCCL watchdog, data loaders) may keep calling CUDA
+            with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode="thread_local"):
+                out = model.forward(d, self.offset_host)
         self.launches = _lib.launch_count() - before   # kernels of ours inside one replay
         pointops.clear_caches()      # entries keyed on the graph's private buffers are of no use to anyone
         self.score, self.pred = out["score"], out["pred"]
         model.backbone.taps = None   # the taps of the capture pass point into the graph's private pool
+        # everything outside the graph's private pool that the captured kernels read: the folded weights of every
+        # module and the constant offset tensors.  Held here so that nothing the replay dereferences can be freed
+        # while this graph is alive; `generation` tells infer_stream when they are no longer the model's current ones.
+        self.keep = [m._frozen for m in model.modules() if isinstance(m, _Freezable)] + list(consts.items)
+        self.generation = _GENERATION[0]
 
     def run(self, coord: torch.Tensor, feat: torch.Tensor):
         """Queue one room on this slot's stream; returns (event, score, pred) with score / pred in
@@ -751,6 +777,10 @@ class OpenSegPTv1(nn.Module):
     MAX_GRAPH_SIGNATURES = 4   # captured size signatures kept alive (each holds `depth` private memory pools)
 
     def _infer_stream_graphs(self, rooms, sig, depth, dev):
+        # graphs captured before the weights / the method / a backend switch changed are stale: drop them
+        for k in [k for k, slots in self._graphs.items()
+                  if any(g.generation != _GENERATION[0] or g.method != self.method for g in slots)]:
+            del self._graphs[k]
         if sig in self._graphs:
             self._graphs[sig] = self._graphs.pop(sig)          # most recently used last
         while len(self._graphs) >= self.MAX_GRAPH_SIGNATURES and sig not in self._graphs:

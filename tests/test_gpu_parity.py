@@ -143,40 +143,36 @@ def test_fps_full_size_80k_to_20k(cuda, oracle):
     assert torch.equal(out.cpu(), ref)
 
 
-@pytest.mark.parametrize("points,layout", [
-    (0, 0), (1, 0), (1, 1),
-    # the 32-group "fine" layout is compiled but has not been run on a GPU yet: POINTOPS_B200_EXPERIMENTAL=1 to try it
-    pytest.param(0, 2, marks=pytest.mark.skipif(os.environ.get("POINTOPS_B200_EXPERIMENTAL") != "1",
-                                                reason="experimental FPS layout (opt-in)"))])
+@pytest.mark.parametrize("variant", ["merge", "chain", "single"])
 @pytest.mark.parametrize("sizes,stride", [([80000], 4), ([52000, 45000], 4), ([100000], 16), ([131072], 64),
                                           ([20000], 4), ([5000, 3000, 2049], 4)])
-def test_fps_chain_layouts_same_result(cuda, oracle, points, layout, sizes, stride):
-    """The chain kernel keeps the points in registers (points 0) or in shared memory as float4 {x, y, z, idx}
-    (points 1), on C CTAs of 256 threads (layout 0, wide) or on C/2 CTAs of 512 threads publishing two candidate
-    groups each (layout 1, tall): same arithmetic, same indices.  131 072 points = the largest
-    scene the resident kernels take (32 points per thread; tall stops at 24 and hands over to wide)."""
-    import pointops
+def test_fps_variants_same_result(cuda, oracle, variant, sizes, stride):
+    """The three schedules of the resident kernel -- merged lists (default), one candidate per CTA (round 1),
+    one sample per exchange -- walk the points in cell order with exact pruning (grid given) or strided (no
+    grid): same arithmetic, same indices.  131 072 points = the largest scene the resident kernels take."""
     from pointcloudpdf_b200 import _lib
+    from pointcloudpdf_b200.pointops import _common as C
+    from pointcloudpdf_b200.pointops.sampling import fps_launch, VARIANTS
     xyz, offset = make_cloud(sizes, 77 + stride, "room")
     new_offset = torch.tensor(np.cumsum([max(s // stride, 1) for s in sizes]), dtype=torch.int32)
     ref = oracle.farthest_point_sampling(xyz, offset, new_offset)
     lib = _lib.load()
-    assert lib.pob_fps_set_points(points) == 0 and lib.pob_fps_set_layout(layout) == 0
-    try:
-        for with_grid in (True, False):          # cell-ordered + pruning, and the strided layout
-            pointops.clear_caches()
-            if with_grid:
-                out = pointops.farthest_point_sampling(xyz.to(cuda), offset.to(cuda), new_offset.to(cuda))
-            else:
-                out = torch.empty(int(new_offset[-1]), dtype=torch.int32, device=cuda)
-                xyz_d, off_d, noff_d = xyz.to(cuda), offset.to(cuda), new_offset.to(cuda)
-                rc = lib.pob_farthest_point_sampling(len(sizes), max(sizes), _lib.ptr(xyz_d), _lib.ptr(off_d), _lib.ptr(noff_d),
-                                                     None, _lib.ptr(out), 0, None, 0, 0.0, _lib.current_stream(cuda))
-                assert rc == 0
-            assert torch.equal(out.cpu(), ref)
-    finally:
-        lib.pob_fps_set_points(-1)
-        lib.pob_fps_set_layout(-1)
+    xyz_d, off_d, noff_d = xyz.to(cuda), offset.to(cuda), new_offset.to(cuda)
+    stats = torch.zeros(2, dtype=torch.int64, device=cuda)
+    for with_grid in (True, False):          # cell-ordered + pruning, and the strided layout
+        C.clear_caches()
+        if with_grid:
+            out = fps_launch(xyz_d, off_d, noff_d, offset.tolist(), new_offset.tolist(), variant=variant, stats=stats)
+        else:
+            out = torch.empty(int(new_offset[-1]), dtype=torch.int32, device=cuda)
+            rc = lib.pob_farthest_point_sampling(len(sizes), max(sizes), _lib.ptr(xyz_d), _lib.ptr(off_d), _lib.ptr(noff_d),
+                                                 None, _lib.ptr(out), 0, None, 0, 0.0, VARIANTS[variant], None,
+                                                 _lib.current_stream(cuda))
+            assert rc == 0
+        assert torch.equal(out.cpu(), ref)
+    if variant != "single":
+        rounds, samples = stats.tolist()
+        assert samples == int(new_offset[-1]) - len(sizes) and 0 < rounds <= samples
 
 
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
@@ -192,7 +188,7 @@ def test_fps_every_cluster_size_same_result(cuda, oracle, cluster):
     for ws, n, cp in ((None, 0, 0.0), (_lib.ptr(grid.workspace), 8000, grid.cell_pts)):  # strided / cell order + pruning
         out.zero_()
         rc = _lib.load().pob_farthest_point_sampling(2, 6000, _lib.ptr(xyz_d), _lib.ptr(off_d), _lib.ptr(noff_d), None,
-                                                     _lib.ptr(out), cluster, ws, n, cp, _lib.current_stream(cuda))
+                                                     _lib.ptr(out), cluster, ws, n, cp, 0, None, _lib.current_stream(cuda))
         assert rc == 0
         assert torch.equal(out.cpu(), ref)
 
