@@ -10,15 +10,23 @@ open-set score -- BASELINE.json configs[1], "openseg-pt-v1-0-msp inference".  Ro
 independent, so N GPUs run N rooms with no data-path collective (weak scaling).
 
 Printed JSON (one line, rank 0):
-  value      whole-job points/s with inputs resident in HBM (CUDA events, max over ranks)
-  e2e        the same through the host-buffer API OpenSegPTv1.infer(): pinned-host -> device copy
+  value      whole-job points/s with inputs resident in HBM.  The K-step schedule is repeated until a timed
+             window lasts >= 0.5 s (a 12-deep room pipeline needs ~25 rooms to fill and drain); every window is
+             bracketed by barrier + synchronize + CUDA events; >= 5 windows; the MEDIAN per rank, then the max
+             over ranks.  `windows` carries every window of rank 0 and the spread.
+  e2e        the same through the host-buffer API OpenSegPTv1.infer_stream(): pinned-host -> device copy
              of coord/feat/offset and device -> host read of score + prediction inside the timing
-  roofline   the kernel of ours with the largest share of the step, timed live with CUDA events
-             on the launching stream inside the timed region (achieved = algorithmic bytes / time)
+  roofline   the DOMINANT kernel of the step (largest share of device time in an instrumented pass with
+             CUDA events around every C-ABI call on its launching stream): FPS, FP32 CUDA-core class, with
+             the brute-force-equivalent and the actually-executed flop rates; `roofline_hbm` = the largest
+             bandwidth-class kernel (the fused layer) as a second entry
   kernels    the same accounting for every C-ABI entry point the step calls
-  cpu_baseline  the reference op sequence on the host cores (oracle port), bounded sample
---impl reference times that CPU port alone (the reference has no CPU implementation of this path
-and its CUDA kernels are not a CPU baseline).
+  ops_cfg1   "kNN + group + aggregate GB/s vs HBM peak" on configs[0]'s shape, forward and backward
+  cfg3_training / cfg5_sharded_knn   (--gpus N > 1) the two other partitioned workloads of BASELINE.json
+  cpu_baseline  the reference op sequence on the host cores (oracle port) on the SAME 80 000-point room
+--impl reference times that CPU port (the reference has no CPU implementation of this path) and, when a GPU
+is visible, adds `gpu_reference_before`: the reference's unmodified model over its own kernels compiled for
+sm_100a (oracle/_ref), i.e. the GPU "before" of the same workload.
 """
 from __future__ import annotations
 
@@ -74,7 +82,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=N_POINTS)
-    ap.add_argument("--cpu-sample-points", type=int, default=8192)
+    ap.add_argument("--cpu-sample-points", type=int, default=N_POINTS,
+                    help="room size of the CPU arm (default: the same 80 000-point room as the GPU arm)")
+    ap.add_argument("--windows", type=int, default=5, help="timed windows per measurement (median reported)")
+    ap.add_argument("--min-window-s", type=float, default=0.5, help="a window repeats the K-step schedule until it lasts this long")
+    ap.add_argument("--no-multi", action="store_true", help="skip cfg3_training / cfg5_sharded_knn when --gpus > 1")
+    ap.add_argument("--no-ops", action="store_true", help="skip the operator-level lines (ops_cfg1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--literal", action="store_true", help="reference op sequence (kNN per block, einsum)")
     ap.add_argument("--linear", default="auto", choices=["auto", "pob", "cublas"],
@@ -212,9 +225,14 @@ def make_sampler(index):
 
 # ------------------------------------------------------------------------------ CPU port --
 
-def cpu_port_points_per_sec(n_points: int, steps: int, warmup: int, threads: int, budget_s: float = 150.0):
+def env_switches():
+    """Every POINTOPS_B200_* variable in effect: recorded in `config` so a run can be reproduced / audited."""
+    return {k: v for k, v in sorted(os.environ.items()) if k.startswith("POINTOPS_B200_")}
+
+
+def cpu_port_points_per_sec(n_points: int, steps: int, warmup: int, threads: int, budget_s: float = 120.0):
     """The reference's op sequence for the same workload on host cores: PTv1 Seg50 (literal path:
-    kNN in every block, gather k and v, einsum) over the oracle's brute-force operators + MSP.
+    kNN in every block, gather k and v, einsum) over the oracle's brute-force operators (C + OpenMP) + MSP.
     This is the one place bench.py executes oracle/ (cpu_baseline / --impl reference)."""
     from oracle import pointops_oracle as O
     from pointcloudpdf_b200 import ptv1, synthetic as S
@@ -232,6 +250,7 @@ def cpu_port_points_per_sec(n_points: int, steps: int, warmup: int, threads: int
         net = ptv1.PointTransformerSeg50(in_channels=IN_CHANNELS, num_classes=NUM_CLASSES).eval().set_fused(False)
         batch = S.s3dis_batch([n_points], seed=2026)
         times = []
+        t_start = time.perf_counter()
         with torch.no_grad():
             for i in range(warmup + steps):
                 t0 = time.perf_counter()
@@ -240,11 +259,62 @@ def cpu_port_points_per_sec(n_points: int, steps: int, warmup: int, threads: int
                 O.msp_score(logits)
                 if i >= warmup:
                     times.append(time.perf_counter() - t0)
-                    if sum(times) > budget_s:   # bounded: a slow host must not turn K steps into an hour
-                        break
+                # bounded: a slow host must not turn K steps into an hour (>= 3 timed steps when they fit)
+                if time.perf_counter() - t_start > budget_s and len(times) >= 1:
+                    break
     finally:
         ptv1.pointops = saved
     return n_points / statistics.median(times), statistics.median(times), len(times)
+
+
+def gpu_reference_before(n_points: int, steps: int = 3):
+    """The GPU "before": the reference's UNMODIFIED PointTransformerSeg50 + MaxProbability (files staged under
+    baseline/_ref) over the reference's OWN kernels compiled for sm_100a (oracle/_ref/libpointops_ref.so behind a
+    pointops._C stub), and the same unmodified callers over this repo's drop-in -- same room, same GPU, eager
+    PyTorch, legacy default stream (the reference's launchers hard-code it).  Reference arm only."""
+    from oracle import ref_glue
+    from pointcloudpdf_b200 import synthetic as S
+    out = {}
+    if not torch.cuda.is_available():
+        return {"unavailable": "no CUDA device visible to the reference arm"}
+    if not ref_glue.available():
+        return {"unavailable": "reference python files neither mounted nor staged under baseline/_ref"}
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    batch = S.s3dis_batch([n_points], seed=2026)
+    d = {k: batch[k].to(dev) for k in ("coord", "feat", "offset")}
+    for backend, key in (("refgpu", "reference_kernels"), ("product", "dropin_kernels_unmodified_callers")):
+        if backend == "refgpu" and not os.path.exists(ref_glue.REF_SO):
+            out[key] = {"unavailable": "oracle/_ref/libpointops_ref.so not built"}
+            continue
+        try:
+            with ref_glue.reference_modules(backend) as R:
+                torch.manual_seed(2024)
+                model = R.ptseg.PointTransformerSeg50(in_channels=IN_CHANNELS, num_classes=NUM_CLASSES).to(dev).eval()
+                rec = R.msp.MaxProbability(method="msp")
+                times = []
+                with torch.no_grad():
+                    for i in range(1 + steps):
+                        if backend == "product":
+                            R.pointops.clear_caches()
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        logits = model(dict(d))
+                        rec.model_hooks = {"backbone": {"forward_output": logits}}
+                        score = rec({})["score"]
+                        torch.cuda.synchronize()
+                        if i >= 1:
+                            times.append(time.perf_counter() - t0)
+            sec = statistics.median(times)
+            out[key] = {"value": n_points / sec, "unit": UNIT, "ms_per_step": sec * 1e3, "timed_steps": len(times)}
+        except Exception as e:   # noqa: BLE001 -- a context number must never take the arm down
+            out[key] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    out["what"] = ("unmodified point_transformer_seg.py + max_probability_v1m1_base.py, eval, f32, one 80 000-point room per step, "
+                   "eager launches on the legacy default stream, wall clock around synchronize; `reference_kernels` = the "
+                   "reference's libs/pointops .cu files compiled unmodified for sm_100a (the GPU 'before'), "
+                   "`dropin_kernels_unmodified_callers` = the same python over this repo's `pointops`")
+    return out
 
 
 def run_reference_arm(args):
@@ -253,17 +323,24 @@ def run_reference_arm(args):
         return
     cores = os.cpu_count() or 1
     n = args.cpu_sample_points
-    pps, sec, timed = cpu_port_points_per_sec(n, max(1, args.steps), max(0, min(args.warmup, 1)), cores)
-    sample = f"one S3DIS-shaped room of {n} points per step (bounded sample of the 80000-point workload; " \
-             f"brute-force kNN/FPS are O(n^2), so points/s at 80000 would be lower); median of {timed} timed steps"
+    pps, sec, timed = cpu_port_points_per_sec(n, max(3, min(args.steps, 8)), max(0, min(args.warmup, 1)), cores)
+    sample = (f"one S3DIS-shaped room of {n} points per step" + (" (the GPU arm's workload)" if n == N_POINTS else
+              " (bounded sample of the 80000-point workload)") + f"; reference op sequence (kNN in every block) over the "
+              f"brute-force C/OpenMP oracle operators + torch CPU linears; median of {timed} timed steps")
     line = {"impl": "reference", "metric": METRIC, "value": pps, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "openseg-pt-v1-0-msp inference, PTv1-Seg50, S3DIS-shaped room", "points_per_step": n,
-                       "classes": NUM_CLASSES},
+            "config": {"workload": "openseg-pt-v1-0-msp inference (BASELINE configs[1]): PTv1-Seg50 + MSP score, "
+                                   "one S3DIS-Area-5-shaped room per step",
+                       "points_per_step_per_gpu": n, "classes": NUM_CLASSES, "in_channels": IN_CHANNELS,
+                       "timed_steps": timed, "env": env_switches()},
             "cpu_baseline": {"value": pps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    try:
+        line["gpu_reference_before"] = gpu_reference_before(N_POINTS)
+    except Exception as e:   # noqa: BLE001
+        line["gpu_reference_before"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     emit(line)
 
 
@@ -271,19 +348,24 @@ def run_reference_arm(args):
 
 def ops_cfg1(dev, hbm_peak):
     """The second half of BASELINE.json's metric -- "kNN + group + aggregate GB/s vs HBM peak" -- on
-    configs[0]'s shape: one 24 000-point S3DIS-shaped cloud, k = 16, C = 32, share_planes = 8.  Each
-    operator is launched 24 times back to back (one CUDA graph, so no host gaps) over 8 rotating argument
-    sets (~60 MB each, > L2 in total) between two CUDA events; GB/s = SURVEY.md 8(d) algorithmic bytes /
-    mean time per launch."""
-    from pointcloudpdf_b200 import synthetic as S
+    configs[0]'s shape: one 24 000-point S3DIS-shaped cloud, k = 16, C = 32, share_planes = 8, forward AND
+    backward.  Each operator is launched 24 times back to back (one CUDA graph, so no host gaps) over 8 rotating
+    argument sets (~60 MB each, > L2 in total) between two CUDA events; GB/s = SURVEY.md 8(d) algorithmic
+    bytes / mean time per launch.  Backward kernels are timed through their C-ABI entry points (the autograd
+    wrappers add allocations that are not the kernel)."""
+    from pointcloudpdf_b200 import synthetic as S, _lib
     import pointcloudpdf_b200.pointops as pointops
+    from pointcloudpdf_b200.pointops import _common as C
     n, k, c, wc = 24000, 16, 32, 4
     b = S.s3dis_batch([n], seed=2025)
     xyz, off = b["coord"].to(dev), b["offset"].to(dev)
     g = torch.Generator(device=dev).manual_seed(0)
     idx, _ = pointops.knn_query(k, xyz, off)
-    sets = [dict(xyz=xyz.clone(), feat=torch.randn(n, c, device=dev, generator=g),
-                 pos=torch.randn(n, k, c, device=dev, generator=g), w=torch.randn(n, k, wc, device=dev, generator=g))
+    sets = [dict(xyz=xyz.clone(), feat=torch.randn(n, c, device=dev, generator=g), feat2=torch.randn(n, c, device=dev, generator=g),
+                 pos=torch.randn(n, k, c, device=dev, generator=g), w=torch.randn(n, k, wc, device=dev, generator=g),
+                 gout=torch.randn(n, k, c, device=dev, generator=g), gout2=torch.randn(n, c, device=dev, generator=g),
+                 gin=torch.zeros(n, c, device=dev), gin2=torch.zeros(n, c, device=dev), gpos=torch.zeros(n, k, c, device=dev),
+                 gw=torch.zeros(n, k, wc, device=dev), gxyz=torch.randn(n, k, 3 + c, device=dev, generator=g))
             for _ in range(8)]
 
     def timed(fn, reps=24):
@@ -308,26 +390,219 @@ def ops_cfg1(dev, hbm_peak):
         return statistics.median(times) / reps * 1e-3
 
     def knn(a):
-        pointops.clear_caches()
+        C.clear_caches()
         pointops.knn_query(k, a["xyz"], off)
 
+    P, cs = _lib.ptr, _lib.current_stream
+
+    def raw(name, *args):
+        return lambda a: _lib.run(name, *[x(a) if callable(x) else x for x in args], cs(dev))
+
+    B4 = 4
+    rows = (
+        ("knn_query k=16 (grid build + query)", knn, 12 * n + 12 * n + 8 * k * n, 8 * n * n),
+        ("grouping with_xyz fwd (knn_query_and_group's gather)", lambda a: pointops.grouping(idx, a["feat"], xyz, xyz, with_xyz=True),
+         B4 * (n * c + 3 * n + 3 * n + n * k + n * k * (3 + c)), 0),
+        ("grouping with_xyz bwd", raw("pob_group_xyz_backward", n, k, c, 1, lambda a: P(a["gxyz"]), P(idx), lambda a: P(a["gin"])),
+         B4 * (n * k * (3 + c) + n * k + n * c), 0),
+        ("grouping2 fwd (feature gather)", lambda a: pointops.grouping2(a["feat"], idx), B4 * (n * c + n * k + n * k * c), 0),
+        ("grouping2 bwd", raw("pob_grouping_backward", n, k, c, lambda a: P(a["gout"]), P(idx), lambda a: P(a["gin"])),
+         B4 * (n * c + n * k + n * k * c), 0),
+        ("subtraction fwd", lambda a: pointops.subtraction(a["feat"], a["feat2"], idx), B4 * (2 * n * c + n * k + n * k * c), 0),
+        ("subtraction bwd", raw("pob_subtraction_backward", n, k, c, P(idx), lambda a: P(a["gout"]), lambda a: P(a["gin"]), lambda a: P(a["gin2"])),
+         B4 * (n * k * c + n * k + 2 * n * c), 0),
+        ("aggregation fwd", lambda a: pointops.aggregation(a["feat"], a["pos"], a["w"], idx),
+         B4 * (n * c + n * k * c + n * k * wc + n * k + n * c), 0),
+        ("aggregation bwd", raw("pob_aggregation_backward", n, k, c, wc, lambda a: P(a["feat"]), lambda a: P(a["pos"]), lambda a: P(a["w"]), P(idx),
+                                lambda a: P(a["gout2"]), lambda a: P(a["gin"]), lambda a: P(a["gpos"]), lambda a: P(a["gw"])),
+         B4 * (n * c + n * k * c + n * k * wc + n * k + n * c) + B4 * (n * c + n * k * c + n * k * wc), 0),
+    )
     out = {}
     with torch.no_grad():
-        for name, fn, nbytes, flops in (
-                ("knn_query k=16 (grid build + query)", knn, 12 * n + 12 * n + 8 * k * n, 8 * n * n),
-                ("grouping with_xyz (knn_query_and_group's gather)", lambda a: pointops.grouping(idx, a["feat"], xyz, xyz, with_xyz=True),
-                 4 * (n * c + 3 * n + 3 * n + n * k + n * k * (3 + c)), 0),
-                ("grouping2 (feature gather)", lambda a: pointops.grouping2(a["feat"], idx), 4 * (n * c + n * k + n * k * c), 0),
-                ("aggregation forward", lambda a: pointops.aggregation(a["feat"], a["pos"], a["w"], idx),
-                 4 * (n * c + n * k * c + n * k * wc + n * k + n * c), 0)):
-            sec = timed(fn)
+        for name, fn, nbytes, flops in rows:
+            try:
+                sec = timed(fn)
+            except Exception as e:   # noqa: BLE001
+                out[name] = {"error": f"{type(e).__name__}: {e}"[:160]}
+                continue
             out[name] = {"us": sec * 1e6, "alg_MB": nbytes / 1e6, "GBps": nbytes / sec / 1e9,
                          "frac_of_hbm_peak": nbytes / sec / 1e9 / hbm_peak}
             if flops:
                 out[name]["bruteforce_equivalent_TFLOPs"] = flops / sec / 1e12
-    pointops.clear_caches()
+    # what the grid kNN really evaluates (one atomicAdd per query warp into a device counter)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    C.clear_caches()
+    C.get_grid(xyz, off).query(k, xyz, off, True, False, stats=cnt)
+    ev = int(cnt.item())
+    kq = out.get("knn_query k=16 (grid build + query)")
+    if kq and "us" in kq:
+        kq["distance_evaluations"] = ev
+        kq["evaluations_per_query"] = ev / n
+        kq["executed_TFLOPs"] = 8 * ev / (kq["us"] * 1e-6) / 1e12
+        kq["note"] = ("bruteforce_equivalent counts 8 flop x n^2 pairs; the grid evaluates evaluations_per_query candidates per "
+                      "query, executed_TFLOPs = 8 flop x those / time (the rest of the time is top-k maintenance and the build)")
+    C.clear_caches()
     return {"shape": "N=24000, k=16, C=32, w_c=4 (BASELINE configs[0])",
-            "timing": "a CUDA graph of 24 back-to-back launches over 8 rotating argument sets, CUDA events around a replay, median of 5", "ops": out}
+            "timing": "a CUDA graph of 24 back-to-back launches over 8 rotating argument sets, CUDA events around a replay, median of 5",
+            "ops": out}
+
+
+# ------------------------------------------------------- the other partitioned workloads --
+
+def cfg3_training(dev, rank, world, dist):
+    """BASELINE configs[2]: PTv1 ScanNet20-shaped training step, 8 scenes x ~95k points, scene-sharded 8/N per
+    rank, DistributedDataParallel (bucketed NCCL all-reduce overlapped with backward, broadcast_buffers=False,
+    as pointcept/engines/defaults.py:22-43 / train.py:218-222), cross-entropy, SGD.  Strong scaling: the batch is
+    fixed; rank 0 also times the whole batch alone (no DDP) in the same process for the 1-GPU base."""
+    from pointcloudpdf_b200 import synthetic as S, sharding
+    from pointcloudpdf_b200.ptv1 import PointTransformerSeg50
+    import pointcloudpdf_b200.pointops as pointops
+    g = torch.Generator().manual_seed(2027)
+    sizes = [int(x) for x in torch.randint(90000, 100001, (8,), generator=g)]
+
+    def make(scene_ids, seed):
+        b = S.scannet_batch([sizes[i] for i in scene_ids], seed=seed)
+        d = {k: b[k].to(dev) for k in ("coord", "feat", "offset")}
+        label = torch.randint(0, 20, (d["coord"].shape[0],), device=dev, generator=torch.Generator(device=dev).manual_seed(seed))
+        return d, label, b["offset"].tolist()
+
+    def timed(step, warm=2, reps=3, sync_ranks=True):
+        for _ in range(warm):
+            step()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            if sync_ranks and world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); step(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    torch.manual_seed(2024)
+    net = PointTransformerSeg50(in_channels=9, num_classes=20).to(dev).train()
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9)
+    mine = sharding.shard_scenes(8, rank, world)
+    d, label, off_host = make(mine, 2027 + rank)
+    model = net
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], broadcast_buffers=False,
+                                                          gradient_as_bucket_view=True)
+
+    def step(sync=True):
+        pointops.clear_caches()
+        opt.zero_grad(set_to_none=True)
+        if world > 1 and not sync:
+            with model.no_sync():
+                torch.nn.functional.cross_entropy(model(d, off_host), label).backward()
+        else:
+            torch.nn.functional.cross_entropy(model(d, off_host), label).backward()
+        opt.step()
+
+    torch.cuda.reset_peak_memory_stats()
+    ms = timed(step)
+    ms_nosync = timed(lambda: step(False), warm=1) if world > 1 else ms
+    peak = torch.cuda.max_memory_allocated() / 2 ** 30
+    t = torch.tensor([ms, ms_nosync], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_nosync = float(t[0]), float(t[1])
+    res = {"scenes_total": 8, "points_total": sum(sizes), "scenes_per_gpu": len(mine), "n_gpus": world,
+           "ms_per_step": ms, "points_per_sec": sum(sizes) / ms * 1e3, "peak_mem_GB_rank0": peak,
+           "ms_per_step_without_allreduce": ms_nosync, "allreduce_exposed_ms": max(ms - ms_nosync, 0.0),
+           "allreduce": "torch DistributedDataParallel over NCCL: 25 MB buckets, all-reduce launched from autograd hooks while "
+                        "backward is still running (overlapped); gradient_as_bucket_view, broadcast_buffers=False" if world > 1 else "none (1 GPU)",
+           "what": "forward + backward (autograd through every pointops kernel) + gradient all-reduce + SGD step, f32, "
+                   "max over ranks of the median of 3 steps"}
+    if world > 1:
+        del model
+        base_ms = None
+        if rank == 0:   # the 1-GPU base of the same batch, same process, no DDP
+            d, label, off_host = make(list(range(8)), 2027)
+            model = net
+
+            def step1():
+                pointops.clear_caches()
+                opt.zero_grad(set_to_none=True)
+                torch.nn.functional.cross_entropy(net(d, off_host), label).backward()
+                opt.step()
+            base_ms = timed(step1, warm=1, reps=3, sync_ranks=False)
+        bt = torch.tensor([base_ms or 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(bt, op=dist.ReduceOp.MAX)
+        base_ms = float(bt[0])
+        res["one_gpu_ms_per_step_same_batch"] = base_ms
+        res["speedup_vs_one_gpu"] = base_ms / ms
+        res["scaling_efficiency"] = base_ms / ms / world
+    del net, opt, d, label
+    torch.cuda.empty_cache()
+    pointops.clear_caches()
+    return res
+
+
+def cfg5_sharded_knn(dev, rank, world, dist):
+    """BASELINE configs[4]: one very large scene, queries sharded over the ranks, reference set replicated, NCCL
+    all-gather of the index / distance shards (pointcloudpdf_b200/sharding.py::sharded_knn_query over the CUDA
+    kernel).  The gathered result must be torch.equal to the single-GPU result."""
+    from pointcloudpdf_b200 import synthetic as S, sharding
+    import pointcloudpdf_b200.pointops as pointops
+    from pointcloudpdf_b200.pointops import _common as C
+    rows = []
+    for n in (1_000_000, 2_000_000):
+        b = S.s3dis_batch([n], seed=2029)
+        xyz, off = b["coord"].to(dev), b["offset"].to(dev)
+        off_host = b["offset"].tolist()
+        for k in (16, 32):
+            def single():
+                C.clear_caches()
+                return C.get_grid(xyz, off).query(k, xyz, off, True, False)[:2]
+
+            def sharded():
+                C.clear_caches()
+                return sharding.sharded_knn_query(k, xyz, off, off_host,
+                                                  knn_fn=lambda ns, x, o, q, qo: C.get_grid(x, o).query(ns, q, qo, True, False)[:2])
+
+            def local_only():   # the rank's share of the queries, no collective
+                C.clear_caches()
+                spans, new_off = sharding.query_slices(off_host, rank, world)
+                q = torch.cat([xyz[a:b_] for a, b_ in spans]).contiguous()
+                return C.get_grid(xyz, off).query(k, q, torch.tensor(new_off, dtype=torch.int32, device=dev), True, False)[:2]
+
+            def timed(fn, reps=5):
+                fn(); torch.cuda.synchronize()
+                ts = []
+                for _ in range(reps):
+                    if world > 1:
+                        dist.barrier()
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); r = fn(); e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                t = torch.tensor([statistics.median(ts)], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return float(t[0]), r
+
+            ms1, ref = timed(single)
+            msN, got = timed(sharded)
+            msL, _ = timed(local_only)
+            equal = bool(torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1]))
+            eq = torch.tensor([1 if equal else 0], device=dev)
+            if world > 1:
+                dist.all_reduce(eq, op=dist.ReduceOp.MIN)
+            rows.append({"n": n, "k": k, "n_gpus": world, "one_gpu_ms": ms1, "sharded_ms": msN, "local_kernel_ms": msL,
+                         "all_gather_and_assembly_ms": max(msN - msL, 0.0), "speedup": ms1 / msN,
+                         "queries_per_sec": n / msN * 1e3, "equal_to_single_gpu": bool(int(eq.item())),
+                         "gathered_MB": 8 * n * k / 1e6})
+            del ref, got
+        del xyz, off
+        torch.cuda.empty_cache()
+    C.clear_caches()
+    return {"rows": rows, "what": "grid build (replicated on every rank) + query of the rank's contiguous slice of the queries + "
+                                  "NCCL all-gather of idx (i32) and dist (f32) + assembly into the (n, k) result on every rank; "
+                                  "CUDA events, median of 5, max over ranks"}
 
 
 # ------------------------------------------------------------------------------- B200 arm --
@@ -344,6 +619,7 @@ def main():
     from pointcloudpdf_b200 import ptv1 as _ptv1
     from pointcloudpdf_b200.ptv1 import OpenSegPTv1
     import pointcloudpdf_b200.pointops as pointops
+    from pointcloudpdf_b200.pointops import sampling as _sampling, _common as _C
     _ptv1.set_linear_backend(args.linear)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -391,21 +667,20 @@ def main():
         h = host[i % n_rooms]
         return net.infer(h["coord"], h["feat"], h["offset"], device=dev)
 
-    class Flushed:
-        """Room sequence for infer_stream that evicts L2 before each room is handed out."""
-        def __init__(self, src, n):
-            self.src, self.n = src, n
-        def __iter__(self):
-            for i in range(self.n):
-                r = self.src[i % n_rooms]
-                yield (r["coord"], r["feat"], r["offset"])
-
     def run_stream(src, n, graphs="auto"):
-        rooms_seq = list(Flushed(src, n))
+        rooms_seq = [(src[i % n_rooms]["coord"], src[i % n_rooms]["feat"], src[i % n_rooms]["offset"]) for i in range(n)]
         last = None
-        for k, (score, pred) in enumerate(net.infer_stream(rooms_seq, depth=depth, device=dev, graphs=graphs)):
+        for score, pred in net.infer_stream(rooms_seq, depth=depth, device=dev, graphs=graphs):
             flush.zero_()                   # L2 eviction on the main stream between rooms
             last = (score, pred)
+        return last
+
+    def run_steps(src, n, graphs="auto"):
+        if depth > 1:
+            return run_stream(src, n, graphs)
+        last = None
+        for i in range(n):
+            last = step_resident(i) if src is resident else step_e2e(i)
         return last
 
     for i in range(W):
@@ -417,65 +692,91 @@ def main():
         run_stream(host, max(W, depth + 2))
     barrier()
 
-    # ---- value: device-resident inputs, K steps, CUDA events on the main stream ----
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def timed_window(src, n, wall=False):
+        """n steps bracketed by barrier + synchronize on both sides, CUDA events on the main stream."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        out = run_steps(src, n)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if wall:
+            ms = max(ms, (time.perf_counter() - t0) * 1e3)
+        return ms, out
+
+    # ---- how often the K-step schedule is repeated inside one timed window: K steps of a 12-deep pipeline are
+    #      mostly fill and drain (47 ms at K = 20), so a window repeats the schedule until it lasts >= min_window_s;
+    #      every rank uses the same count (max over ranks of the calibration) ----
+    calib_ms, _ = timed_window(resident, max(K, depth + 2))
+    est_step = calib_ms / max(K, depth + 2)
+    t = torch.tensor([est_step], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    est_step = float(t[0])
+    repeats = max(1, int(-(-args.min_window_s * 1e3 // (K * est_step))))
+    M = K * repeats
+    n_win = max(1, args.windows)
+
     with make_sampler(local if rank == 0 else None) as clocks:
         # the sampler's start-up (NVML attach, up to a second) leaves the GPU idle and its clocks parked: a short
         # untimed burst of the same schedule brings them back before the clock starts (W warm-up steps were done above)
-        if depth > 1:
-            run_stream(resident, depth + 2)
-        else:
-            step_resident(0)
+        run_steps(resident, depth + 2)
         barrier()
         launches0 = _lib.launch_count()
-        e0.record()
-        if depth > 1:
-            run_stream(resident, K)
-        else:
-            for i in range(K):
-                step_resident(i)
-        e1.record()
-        barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - launches0
+        win_ms = [timed_window(resident, M)[0] for _ in range(n_win)]
+        launches = (_lib.launch_count() - launches0) / n_win
+        # ---- e2e: host buffers in, host score out ----
+        e2e_ms = []
+        for _ in range(n_win):
+            ms, (score, pred) = timed_window(host, M, wall=True)
+            e2e_ms.append(ms)
 
-    # ---- the same K steps once more with a CUDA-event bracket around every C-ABI call (on the
+    # ---- the same schedule once more with a CUDA-event bracket around every C-ABI call (on the
     #      stream it launches on): attributes the step to kernels; its own wall time is reported
     #      separately because ~250 event records per room are not free ----
+    KP = min(K, 48)
     prof = _lib.OpProfile()
     _lib.PROFILE = prof
     barrier()
     p0_, p1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0_.record()
-    if depth > 1:
-        run_stream(resident, K, graphs=False)   # eager launches: the C-ABI calls are what the events bracket
-    else:
-        for i in range(K):
-            step_resident(i)
+    run_steps(resident, KP, graphs=False)   # eager launches: the C-ABI calls are what the events bracket
     p1_.record()
     barrier()
     _lib.PROFILE = None
     ms_profiled = p0_.elapsed_time(p1_)
     ops = prof.summary()
 
-    # ---- e2e: host buffers in, host score out ----
-    barrier()
-    t0 = time.perf_counter()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    if depth > 1:
-        score, pred = run_stream(host, K)
-    else:
-        for i in range(K):
-            score, pred = step_e2e(i)
-    e3.record()
-    barrier()
-    e2e_ms_total = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
+    # ---- what FPS / kNN really execute in one room (device counters, outside any timed region) ----
+    fps_stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    knn_stats = torch.zeros(1, dtype=torch.int64, device=dev)
+    _sampling.STATS, _C.KNN_STATS = fps_stats, knn_stats
+    pointops.clear_caches()
+    with torch.no_grad():
+        net(resident[0], off_host[0])
+    torch.cuda.synchronize()
+    _sampling.STATS, _C.KNN_STATS = None, None
+    fps_rounds, fps_samples, fps_evals, _ = fps_stats.tolist()
+    knn_evals = int(knn_stats.item())
 
-    t = torch.tensor([ms_total, e2e_ms_total], dtype=torch.float64, device=dev)
+    med = statistics.median
+    t = torch.tensor([med(win_ms), med(e2e_ms), max(win_ms), -min(win_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms_total = float(t[0]), float(t[1])
+    ms_window, e2e_window, ms_worst, ms_best = float(t[0]), float(t[1]), float(t[2]), -float(t[3])
+
+    multi = {}
+    if world > 1 and not args.no_multi:
+        try:
+            multi["cfg3_training"] = cfg3_training(dev, rank, world, dist)
+        except Exception as e:   # noqa: BLE001 -- a side workload must not take the headline line down
+            multi["cfg3_training"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        try:
+            multi["cfg5_sharded_knn"] = cfg5_sharded_knn(dev, rank, world, dist)
+        except Exception as e:   # noqa: BLE001
+            multi["cfg5_sharded_knn"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
         peaks = {}
@@ -485,62 +786,67 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        step_ms = ms_total / K
+        step_ms = ms_window / M
+        clk = clocks.summary()
+        sm_hz = (clk.get("sm_mhz") or 1965.0) * 1e6
+        fp32_peak = 148 * 128 * 2 * sm_hz / 1e12
         kernels = {}
         for name, d in sorted(ops.items(), key=lambda kv: -kv[1]["ms"]):
             per_call_ms = d["ms"] / d["calls"]
             gbs = d["alg_bytes"] / d["calls"] / (per_call_ms * 1e-3) / 1e9 if per_call_ms > 0 else 0.0
-            kernels[name] = {"calls_per_step": d["calls"] / K, "ms_per_step": d["ms"] / K,
+            kernels[name] = {"calls_per_step": d["calls"] / KP, "ms_per_step": d["ms"] / KP,
                              "share_of_step": d["ms"] / ms_profiled, "alg_MB_per_call": d["alg_bytes"] / d["calls"] / 1e6,
                              "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
                              "alg_GFLOP_per_call": d["alg_flops"] / d["calls"] / 1e9,
                              "achieved_TFLOPs": d["alg_flops"] / d["calls"] / (per_call_ms * 1e-3) / 1e12 if per_call_ms > 0 else 0.0}
-        # FPS is the largest kernel by time but it is a serial dependent chain on 16 SMs (latency-bound: no
-        # byte or flop roofline describes it; its accounting is reported as `dominant_kernel`).  `roofline`
-        # is the largest bandwidth-class kernel of the step: the fused group + aggregate layer.
         traffic = {}
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
         except (OSError, ValueError):
             pass
-        # FP32-issue / latency class kernels (their byte roofline says nothing): FPS, kNN, the linears
-        bw_class = [k for k in kernels if k not in ("pob_farthest_point_sampling", "pob_knn_grid_query", "pob_knn_grid_build",
-                                                    "pob_linear_forward")]
-        top = bw_class[0] if bw_class else None
-        roof = None
-        if top:
-            kd = kernels[top]
-            tr = traffic.get(top, {})
-            roof = {"kernel": top, "bound": "hbm", "achieved": kd["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kd["frac_of_hbm_peak"], "traffic": tr.get("dram_bytes_per_launch"),
-                    "traffic_source": tr.get("source"), "peak_source": peak_src,
-                    "share_of_step": kd["share_of_step"], "avg_launch_ms": kd["ms_per_step"] / kd["calls_per_step"],
-                    "alg_bytes_per_launch": kd["alg_MB_per_call"] * 1e6,
-                    "unfused_operator_equivalent": {
-                        "bytes_per_launch": ops[top]["unfused_bytes"] / ops[top]["calls"],
-                        "GBps": ops[top]["unfused_bytes"] / ops[top]["calls"] / (kd["ms_per_step"] / kd["calls_per_step"] * 1e-3) / 1e9,
-                        "what": "SURVEY.md 8(d) algorithmic bytes of the reference operators one launch replaces (knn_query_and_group "
-                                "gather of k with xyz + grouping of v + aggregation forward) / the same launch time: the traffic "
-                                "fusion removed, for context -- NOT bytes this kernel moves"} if ops[top].get("unfused_bytes") else None,
-                    "note": "achieved = compulsory bytes of the FUSED op (q, k, v, out rows, indices, coordinates once) / "
-                            "mean launch time by CUDA events in the instrumented pass; the (n, ns, C) tensors the unfused "
-                            "reference ops would move are never materialised, so the kernel is bound by L2 gathers and FP32 "
-                            "issue, not HBM (profiles/)"}
-        dominant = None
-        if kernels:
-            name = next(iter(kernels))
+        fp32_class = ("pob_farthest_point_sampling", "pob_knn_grid_query", "pob_knn_grid_build", "pob_linear_forward")
+
+        def roof_entry(name):
             kd = kernels[name]
-            clk = (clocks.summary().get("sm_mhz") or 1965.0) * 1e6
-            fp32_peak = 148 * 128 * 2 * clk / 1e12
-            tf = kd["alg_GFLOP_per_call"] / (kd["ms_per_step"] / kd["calls_per_step"]) if kd["ms_per_step"] > 0 else 0.0
-            dominant = {"kernel": name, "bound": "latency (serial chain; FP32 CUDA cores)", "share_of_step": kd["share_of_step"],
-                        "avg_launch_ms": kd["ms_per_step"] / kd["calls_per_step"],
-                        "bruteforce_equivalent_TFLOPs": tf, "fp32_peak_TFLOPs": fp32_peak, "frac_of_fp32_peak": tf / fp32_peak,
-                        "note": "exact pruning skips ~95 % of the distance updates the flop count assumes; the kernel runs on "
-                                "one 16-CTA cluster and overlaps other rooms' kernels (share_of_step can exceed 1)"}
+            launch_ms = kd["ms_per_step"] / kd["calls_per_step"]
+            if name in fp32_class:
+                r = {"kernel": name, "bound": "fp32", "achieved": kd["achieved_TFLOPs"], "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": kd["achieved_TFLOPs"] / fp32_peak, "traffic": None,
+                     "peak_source": f"148 SMs x 128 FP32 lanes x 2 flop x {sm_hz / 1e6:.0f} MHz (median SM clock sampled during the timed "
+                                    f"region; MEASURED_PEAKS.json carries no FP32 figure)",
+                     "alg_GFLOP_per_launch": kd["alg_GFLOP_per_call"]}
+                if name == "pob_farthest_point_sampling":
+                    real = 10.0 * fps_evals / 4 / (launch_ms * 1e-3) / 1e12 if launch_ms > 0 else 0.0   # 4 launches per room
+                    r.update({"achieved_is": "SURVEY.md 8(d) algorithmic flops, 10 x sum (m-1) x n brute-force-equivalent, / mean launch time",
+                              "executed_TFLOPs": real, "executed_frac": real / fp32_peak,
+                              "executed_is": "10 flop x point distances the kernel really evaluated (device counter; exact pruning skips the rest)",
+                              "rounds_per_room": fps_rounds, "samples_per_room": fps_samples,
+                              "samples_per_exchange": fps_samples / max(fps_rounds, 1),
+                              "class": "latency: m - 1 dependent argmax steps; the merged-list kernel commits samples_per_exchange of "
+                                       "them per cluster-wide exchange on one 16-CTA cluster",
+                              "variant": os.environ.get("POINTOPS_B200_FPS", "auto")})
+            else:
+                tr = traffic.get(name, {})
+                r = {"kernel": name, "bound": "hbm", "achieved": kd["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                     "frac": kd["frac_of_hbm_peak"], "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
+                     "peak_source": peak_src, "alg_bytes_per_launch": kd["alg_MB_per_call"] * 1e6}
+                if ops[name].get("unfused_bytes"):
+                    r["unfused_operator_equivalent"] = {
+                        "bytes_per_launch": ops[name]["unfused_bytes"] / ops[name]["calls"],
+                        "GBps": ops[name]["unfused_bytes"] / ops[name]["calls"] / (launch_ms * 1e-3) / 1e9,
+                        "what": "SURVEY.md 8(d) bytes of the reference operators one launch replaces / the same launch time: traffic "
+                                "fusion removed, for context -- NOT bytes this kernel moves"}
+            r.update({"share_of_step": kd["share_of_step"], "avg_launch_ms": launch_ms,
+                      "timed": "CUDA events around every launch on its launching stream, instrumented eager pass of the same schedule "
+                               "(rooms in flight concurrently: launch times include contention)"})
+            return r
+
+        roof = roof_entry(next(iter(kernels))) if kernels else None
+        bw = [k for k in kernels if k not in fp32_class]
+        roof_hbm = roof_entry(bw[0]) if bw else None
         h2d = sum(v.numel() * v.element_size() for v in host[0].values())
         d2h = score.numel() * score.element_size() + pred.numel() * pred.element_size()
-        line = {"metric": METRIC, "value": world * args.points * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+        line = {"metric": METRIC, "value": world * args.points * M / (ms_window * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "openseg-pt-v1-0-msp inference (BASELINE configs[1]): PTv1-Seg50 + fused MSP score, "
@@ -548,33 +854,43 @@ def main():
                            "points_per_step_per_gpu": args.points, "classes": NUM_CLASSES, "in_channels": IN_CHANNELS,
                            "op_sequence": "literal (kNN per block, einsum)" if args.literal else
                                           "one kNN per stage + fused aggregation kernel",
-                           "linears": {"pob": "pob_linear_forward (FP32 FFMA tiles, bias / skip / ReLU on the accumulators)",
-                                       "cublas": "cuBLAS through torch (SIMT sgemm + cuBLASLt bias pass)",
-                                       "auto": "per shape: pob_linear_forward for linears with a bias / skip / ReLU epilogue and the "
-                                               "80000-row layers, cuBLAS for the plain q/k/v GEMMs of the deeper stages"}[args.linear],
+                           "linears": args.linear,
                            "l2": "256 MiB memset between timed iterations (inside the timed region)",
+                           "timed_window": f"{repeats} x the {K}-step schedule = {M} steps per window (>= {args.min_window_s} s), "
+                                           f"{n_win} windows, each bracketed by barrier + synchronize + CUDA events; value = median "
+                                           f"window per rank, max over ranks",
                            "schedule": (f"rooms served in order by OpenSegPTv1.infer_stream, {depth} in flight: each room is one "
                                         f"CUDA-graph replay (coordinate branch: FPS + kNN, forked; feature branch; joined) on "
-                                        f"its own stream, so the serial FPS chains of the next rooms run under the feature "
-                                        f"path of the current one; every room is computed in full inside the timed region") if depth > 1
+                                        f"its own stream; every room is computed in full inside the timed region") if depth > 1
                                        else "one room at a time (geometry side stream within the room)",
-                           "parallelism": f"scene-sharded x{world}, no data-path collective"},
-                "e2e": {"value": world * args.points * K / (e2e_ms_total * 1e-3), "unit": UNIT,
-                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_total / K},
-                "gpu_launches": launches, "gpu_launches_per_step": launches / K,
-                "kernel_attribution": {"how": "second pass of the same K steps, launched eagerly (no graph replay), with CUDA events around every C-ABI call; "
-                                              "with rooms in flight concurrently, kernel times overlap and shares can sum past 1",
-                                       "ms_per_step_instrumented": ms_profiled / K},
-                "roofline": roof, "dominant_kernel": dominant, "kernels": kernels, "clocks": clocks.summary()}
-        line["ops_cfg1"] = ops_cfg1(dev, hbm_peak)
+                           "parallelism": f"scene-sharded x{world}, no data-path collective",
+                           "env": env_switches()},
+                "windows": {"steps_per_window": M, "n": n_win, "ms_rank0": win_ms, "e2e_ms_rank0": e2e_ms,
+                            "spread_rel_max_over_ranks": (ms_worst - ms_best) / ms_window if ms_window > 0 else None},
+                "e2e": {"value": world * args.points * M / (e2e_window * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_window / M},
+                "gpu_launches": launches / repeats, "gpu_launches_per_step": launches / M,
+                "kernel_attribution": {"how": f"{KP} steps of the same schedule launched eagerly (no graph replay) with CUDA events around every "
+                                              "C-ABI call; with rooms in flight concurrently kernel times overlap and shares can sum past 1",
+                                       "ms_per_step_instrumented": ms_profiled / KP},
+                "roofline": roof, "roofline_hbm": roof_hbm,
+                "knn_per_room": {"distance_evaluations": knn_evals, "executed_GFLOP": 8 * knn_evals / 1e9,
+                                 "what": "candidates all grid kNN launches of one room evaluated (device counter)"},
+                "kernels": kernels, "clocks": clk}
+        line.update(multi)
+        if not args.no_ops:
+            try:
+                line["ops_cfg1"] = ops_cfg1(dev, hbm_peak)
+            except Exception as e:   # noqa: BLE001
+                line["ops_cfg1"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n = args.cpu_sample_points
-            pps, sec, _ = cpu_port_points_per_sec(n, 3, 1, cores)
+            pps, sec, timed_n = cpu_port_points_per_sec(n, 3, 0, cores, budget_s=60.0)
             line["cpu_baseline"] = {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"one {n}-point S3DIS-shaped room, reference op sequence over the "
-                                              f"brute-force oracle operators, {sec:.2f} s per room (O(n^2): an "
-                                              f"80000-point room would be slower per point)"}
+                                    "sample": f"one {n}-point S3DIS-shaped room (the GPU arm's workload), reference op sequence over "
+                                              f"the brute-force C/OpenMP oracle operators + torch CPU linears, {sec:.2f} s per room, "
+                                              f"median of {timed_n} steps"}
         emit(line)
     if world > 1:
         dist.barrier()

@@ -57,10 +57,12 @@ int pob_knn_grid_build(int64_t n, int b, const float* xyz, const int* offset, fl
                        void* workspace, size_t workspace_bytes, cudaStream_t stream);
 /* Query a built grid (reusable for any new_xyz / nsample against the same xyz, offset).
  * weight (m, nsample), optional: fused inverse-distance weights of
- * functions/interpolation.py:15-17, w = r / sum(r), r = 1 / (sqrt(d2) + 1e-8).               */
+ * functions/interpolation.py:15-17, w = r / sum(r), r = 1 / (sqrt(d2) + 1e-8).
+ * stats_u64, optional (else NULL): device uint64 the launch adds the number of candidate distances it
+ * actually evaluated to (the grid visits a few hundred per query; brute force would visit n_scene).  */
 int pob_knn_grid_query(int64_t m, int nsample, int64_t n, int b, const float* xyz, const float* new_xyz,
                        const int* new_offset, float cell_pts, const void* workspace, int* idx, float* dist,
-                       float* weight, int take_sqrt, cudaStream_t stream);
+                       float* weight, int take_sqrt, void* stats_u64, cudaStream_t stream);
 /* Build + query in one call, cell_pts = 2; workspace >= pob_knn_grid_workspace_bytes(n, b, 2). */
 int pob_knn_query(int64_t m, int nsample, int64_t n, int b, const float* xyz, const float* new_xyz,
                   const int* offset, const int* new_offset, int* idx, float* dist, int take_sqrt,
@@ -116,9 +118,10 @@ int pob_random_ball_query(int64_t m, int nsample, float min_radius, float max_ra
  *                      exchange accepts the exact global prefix (~20 samples per exchange on room-shaped clouds)
  *   POB_FPS_CHAIN  (2) round-1 kernel: one candidate + bound per CTA and exchange (~4.5 samples per exchange)
  *   POB_FPS_SINGLE (3) one sample per exchange
- * stats_u64x2: NULL, or a device pointer to 2 x uint64 {rounds, samples} the launch accumulates into
- * (mean samples accepted per cluster-wide exchange = samples / rounds).  Per-call arguments: the library keeps
- * no tuning state between calls.                                                                          */
+ * stats_u64x4: NULL, or a device pointer to 4 x uint64 {rounds, samples, point distances evaluated, reserved}
+ * the launch accumulates into (mean samples accepted per cluster-wide exchange = samples / rounds; the third
+ * counter is filled by the MERGE variant only).  Per-call arguments: the library keeps no tuning state
+ * between calls.                                                                                          */
 #define POB_FPS_AUTO 0
 #define POB_FPS_MERGE 1
 #define POB_FPS_CHAIN 2
@@ -126,7 +129,7 @@ int pob_random_ball_query(int64_t m, int nsample, float min_radius, float max_ra
 int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, const int* offset,
                                 const int* new_offset, float* tmp, int* idx, int cluster_hint,
                                 const void* grid_workspace, int64_t n, float cell_pts, int variant,
-                                void* stats_u64x2, cudaStream_t stream);
+                                void* stats_u64x4, cudaStream_t stream);
 
 /* --------------------------------------------------------- grouping (pointops.grouping2) --
  * grouping_{forward,backward}_cuda_launcher (src/grouping/grouping_cuda_kernel.h:14-15).

@@ -115,9 +115,16 @@ def _make_C_stub_refgpu() -> types.ModuleType:
     def interpolation_backward_cuda(n, c, k, grad_output, idx, weight, grad_input):
         L.interpolation_backward_cuda_launcher(I(n), I(c), I(k), g(grad_output.contiguous()), g(idx), g(weight), g(grad_input))
 
+    def _unsupported(*a, **k):
+        raise NotImplementedError("not on the PTv1 hot path (SURVEY.md section 8 f-4)")
+
     for name, fn in list(locals().items()):
         if name.endswith("_cuda"):
             setattr(C, name, fn)
+    for name in ("ball_query_cuda", "random_ball_query_cuda", "attention_relation_step_forward_cuda",
+                 "attention_relation_step_backward_cuda", "attention_fusion_step_forward_cuda",
+                 "attention_fusion_step_backward_cuda"):
+        setattr(C, name, _unsupported)
     return C
 
 

@@ -26,7 +26,7 @@ SIGNATURES = {
     "pob_error_string": (ctypes.c_char_p, [I]),
     "pob_knn_grid_workspace_bytes": (Z, [L, I, F]),
     "pob_knn_grid_build": (I, [L, I, P, P, F, P, Z, P]),
-    "pob_knn_grid_query": (I, [L, I, L, I, P, P, P, F, P, P, P, P, I, P]),
+    "pob_knn_grid_query": (I, [L, I, L, I, P, P, P, F, P, P, P, P, I, P, P]),
     "pob_knn_query": (I, [L, I, L, I, P, P, P, P, P, P, I, P, Z, P]),
     "pob_knn_query_bruteforce": (I, [L, I, I, P, P, P, P, P, P, I, P, Z, P]),
     "pob_ball_query": (I, [L, I, F, F, L, I, P, P, P, F, P, P, P, P, P]),

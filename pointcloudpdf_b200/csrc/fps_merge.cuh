@@ -17,9 +17,12 @@
 //     true maximum is <= the value of its first not-yet-taken list entry (min-distances only decrease), which
 //     sorts after e_j; e_j itself is untouched, so it is the global maximum, lowest index among ties.
 //     The walk stops at the first terminal or conflict; at most 32 samples are taken per exchange;
-//   * afterwards a warp applies to pt[] only the accepted samples whose reach intersects its bounding box
-//     (exact, conservatively rounded -- as in the round-1 kernels).  If one of them came from another warp its
-//     list is void: st = pt, D local steps again.  If only its own entries were taken the list just shifts.
+//   * afterwards a warp applies only the accepted samples whose reach intersects its bounding box (exact,
+//     conservatively rounded -- as in the round-1 kernels): its own ones to pt[] (st[] has them already), foreign
+//     ones to pt[] AND st[].  The list stays valid as long as no foreign sample lowers one of its pending entries
+//     (a point test per entry and sample): entries taken by the merge are popped, one local step per popped entry
+//     tops the list up again.  Only when a pending entry IS lowered the list is void: st = pt, D local steps
+//     (5 of 128 warps per round at 80 000 points; restarting on every touch would hit 60).
 //
 // Two-level merge: a CTA ranks its 8 x (D+1) warp entries and publishes the top KC (+ the next one as its
 // terminal) to all CTAs of the cluster with st.async + mbarrier (32-byte entries); every CTA then ranks the
@@ -66,9 +69,10 @@ __device__ __forceinline__ FpsEnt ent_load(const FpsEnt* src) {
 template <int P>
 __device__ __forceinline__ void fps_warp_argmax(const float (&st)[P], const float4* __restrict__ warp_pts, int lane,
                                                 unsigned& nb, int& ni, float& nx, float& ny, float& nz) {
-    float m = 0.f;   // padding slots hold -1 and never win
+    float m4[4] = {0.f, 0.f, 0.f, 0.f};   // padding slots hold -1 and never win; four chains, not one of length P
 #pragma unroll
-    for (int p = 0; p < P; p++) m = fmaxf(m, st[p]);
+    for (int p = 0; p < P; p++) m4[p & 3] = fmaxf(m4[p & 3], st[p]);
+    const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
     const unsigned mb = __float_as_uint(m);
     nb = __reduce_max_sync(FULL, mb);
     int cand = INT_MAX, cp = 0;
@@ -89,18 +93,58 @@ __device__ __forceinline__ void fps_warp_argmax(const float (&st)[P], const floa
     nx = q.x; ny = q.y; nz = q.z;
 }
 
+// rows of register slots the sample (sx, sy, sz) can lower, given that every value in the warp is <= bound:
+// lane p tests row p's box (same conservative rounding as the warp-level test)
+template <int P>
+__device__ __forceinline__ unsigned fps_row_mask(const float (&rlo)[3], const float (&rhi)[3], float sx, float sy, float sz,
+                                                 float bound, int lane) {
+    const float ex = fmaxf(fmaxf(rlo[0] - sx, sx - rhi[0]), 0.f);
+    const float ey = fmaxf(fmaxf(rlo[1] - sy, sy - rhi[1]), 0.f);
+    const float ez = fmaxf(fmaxf(rlo[2] - sz, sz - rhi[2]), 0.f);
+    const float b2 = __fmaf_rn(ez, ez, __fmaf_rn(ex, ex, __fmul_rn(ey, ey)));
+    return __ballot_sync(FULL, lane < P && !(b2 * 0.99999f >= bound));
+}
+
+// d2 of this lane's point of row p against (sx, sy, sz): coordinates from registers, or (SP) from shared memory
+#define POB_FPS_D2(p, sx, sy, sz) \
+    (SP ? [&] { const float4 q_ = warp_pts[(p) * 32 + lane]; return d2_ref(q_.x, q_.y, q_.z, sx, sy, sz); }() \
+        : d2_ref(px[SP ? 0 : (p)], py[SP ? 0 : (p)], pz[SP ? 0 : (p)], sx, sy, sz))
+
+// for every row p whose bit is set in `mask` (warp-uniform): BODY with the compile-time index p; rows are skipped
+// four at a time
+#define POB_FPS_FOR_ROWS(mask, BODY)                                            \
+    _Pragma("unroll") for (int g_ = 0; g_ < P; g_ += 4) {                       \
+        if ((mask) & (0xFu << g_)) {                                            \
+            _Pragma("unroll") for (int p = g_; p < (g_ + 4 < P ? g_ + 4 : P); p++) { \
+                if ((mask) & (1u << p)) { BODY }                                \
+            }                                                                   \
+        }                                                                       \
+    }
+
 // One cluster of C CTAs (T = 256 threads) per scene; P points per thread in registers; D list entries per warp;
 // KC entries per CTA and exchange.  Dynamic shared memory: float4 {x, y, z, idx}[T * P].
-template <int P, int T, int D, int KC>
-__global__ void __launch_bounds__(T, 1)
-fps_merge_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
-                 const SceneGrid* __restrict__ scenes, const int* __restrict__ cell_start,
-                 const float4* __restrict__ sorted, int* __restrict__ idx, unsigned long long* __restrict__ stats) {
-    cg::cluster_group cluster = cg::this_cluster();
-    const int C = (int)cluster.num_blocks();
-    int rank;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-    const int scene = blockIdx.x / C;
+//
+// GX = true is the GRID-WIDE form for scenes beyond what one cluster holds in registers (131 072 points): one
+// cooperative launch of G <= 148 CTAs per scene (1.2 M points at 32 per thread), same lists, same merge rule.  The
+// exchange goes through global memory instead of DSMEM -- every CTA writes its message to gmsg[parity][cta],
+// arrives on a monotonic counter (release) and spins until all G have (acquire); then all G * (KC + 1) entries are
+// staged in shared memory.  Ranking 740 entries by counting would cost 2 000 compares per thread, so it is
+// thresholded first: T* = the largest "first terminal" key of any CTA is where the walk must stop anyway, only
+// real entries above it (a few dozen) are compacted and ranked.
+template <int P, int T, int D, int KC, bool GX, bool SP>
+__device__ __forceinline__ void
+fps_merge_body(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
+               const SceneGrid* __restrict__ scenes, const int* __restrict__ cell_start,
+               const float4* __restrict__ sorted, int* __restrict__ idx, unsigned long long* __restrict__ stats,
+               int scene_arg, int cap_points, FpsEnt* __restrict__ gmsg, unsigned* __restrict__ gcounter) {
+    int C, rank, scene;
+    if constexpr (GX) {
+        C = (int)gridDim.x; rank = (int)blockIdx.x; scene = scene_arg;
+    } else {
+        C = (int)cg::this_cluster().num_blocks();
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+        scene = blockIdx.x / C;
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = T / 32;                 // warps per CTA
     constexpr int WL = D + 1;                  // entries of a warp list (D real + terminal)
@@ -116,21 +160,36 @@ fps_merge_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
     const int s_n = scene == 0 ? 0 : offset[scene - 1], e_n = offset[scene];
     const int s_m = scene == 0 ? 0 : new_offset[scene - 1], e_m = new_offset[scene];
 
-    extern __shared__ __align__(16) float4 s_pts[];            // [T * P] {x, y, z, idx}
+    extern __shared__ __align__(16) float4 s_pts[];            // [T * P] {x, y, z, idx}; GX: then FpsEnt[C * ME], u16[C * ME]
     __shared__ __align__(16) FpsEnt s_wl[CE];                  // warp lists, WL entries each
     __shared__ __align__(16) FpsEnt s_cs[ME];                  // this CTA's message
-    __shared__ __align__(16) FpsEnt s_msg[2][NSLOT];           // messages of all CTAs, by round parity
+    __shared__ __align__(16) FpsEnt s_msg_store[GX ? 1 : 2 * NSLOT];   // cluster form: messages of all CTAs, by round parity
+    FpsEnt (*s_msg)[NSLOT] = reinterpret_cast<FpsEnt (*)[NSLOT]>(s_msg_store);
+    FpsEnt* const s_all = reinterpret_cast<FpsEnt*>(s_pts + T * P);                    // GX: all C * ME entries of the round
+    unsigned short* const s_cand = reinterpret_cast<unsigned short*>(s_all + C * ME);   // GX: indices of the entries above T*
+    __shared__ unsigned long long s_red[NW];
+    __shared__ int s_cnt;
     __shared__ __align__(16) FpsEnt s_sorted[LMAX];            // merged order (top LMAX); [0, L) = accepted samples
-    __shared__ int s_fail[2];                                  // first position that is not accepted, by parity
+    __shared__ __align__(16) unsigned s_failw[2][NW];          // per warp: which of its four positions are not accepted
     __shared__ __align__(8) unsigned long long s_bar[2];
 
-    if (e_m <= s_m || e_n <= s_n) return;  // uniform over the cluster
+    if (e_m <= s_m || e_n <= s_n) return;  // uniform over the cluster / grid
     const int n = e_n - s_n;
     const int total = e_m - s_m;
+    // a call with scenes on both sides of the cluster capacity launches both forms; each takes its own scenes
+    if (GX ? n <= cap_points : n > C * T * P) return;
 
     const bool in_cells = scenes != nullptr && scenes[scene].use_grid;
-    float px[P], py[P], pz[P], pt[P], st[P];
+    // SP (shared-memory points): the coordinates are read from the float4 copy in shared memory where they are used
+    // instead of living in 3 * P registers -- with row pruning an update touches a few rows only, so the extra LDS.128
+    // per row is noise, and at <= 128 registers a second CTA (another room's FPS cluster, or the feature path's
+    // kernels) fits on the SM next to this latency-bound one
+    constexpr int PR = SP ? 1 : P;
+    float px[PR], py[PR], pz[PR], pt[P], st[P];
     float blo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, bhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    // second pruning level: lane p < P keeps the bounding box of ROW p = the 32 consecutive points (one per lane)
+    // of register slot p -- in cell order that is a patch of a few cells, far tighter than the warp's box
+    float rlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, rhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     bool box_ok = true;
     const int sbase = in_cells ? __ldg(cell_start + scenes[scene].cell_base) : 0;
     float4* const warp_pts = s_pts + warp * P * 32;
@@ -157,8 +216,25 @@ fps_merge_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
             pt[p] = -1.f;  // never a maximum: fminf keeps it at -1
         }
         st[p] = pt[p];
-        px[p] = vx; py[p] = vy; pz[p] = vz;
+        if constexpr (!SP) { px[p] = vx; py[p] = vy; pz[p] = vz; }
         warp_pts[p * 32 + lane] = make_float4(vx, vy, vz, __int_as_float(vi));
+        {
+            const bool real = pos < n;
+            float l3[3] = {real ? vx : FLT_MAX, real ? vy : FLT_MAX, real ? vz : FLT_MAX};
+            float h3[3] = {real ? vx : -FLT_MAX, real ? vy : -FLT_MAX, real ? vz : -FLT_MAX};
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    l3[a] = fminf(l3[a], __shfl_xor_sync(FULL, l3[a], o));
+                    h3[a] = fmaxf(h3[a], __shfl_xor_sync(FULL, h3[a], o));
+                }
+            }
+            if (lane == p) {
+#pragma unroll
+                for (int a = 0; a < 3; a++) { rlo[a] = l3[a]; rhi[a] = h3[a]; }
+            }
+        }
     }
 #pragma unroll
     for (int a = 0; a < 3; a++) {
@@ -173,11 +249,12 @@ fps_merge_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
     // every slot starts EMPTY: key 0 (below every real key), terminal, owner -1
     {
         const uint4 z0 = make_uint4(0u, 0u, 0xffffffffu, 0u), z1 = make_uint4(0u, 0u, 0u, 0u);
-        for (int i = tid; i < 2 * NSLOT; i += T) { reinterpret_cast<uint4*>(&s_msg[0][0])[2 * i] = z0; reinterpret_cast<uint4*>(&s_msg[0][0])[2 * i + 1] = z1; }
+        if constexpr (!GX)
+            for (int i = tid; i < 2 * NSLOT; i += T) { reinterpret_cast<uint4*>(&s_msg[0][0])[2 * i] = z0; reinterpret_cast<uint4*>(&s_msg[0][0])[2 * i + 1] = z1; }
+        if (tid == 0) s_cnt = 0;
         for (int i = tid; i < CE; i += T) { reinterpret_cast<uint4*>(s_wl)[2 * i] = z0; reinterpret_cast<uint4*>(s_wl)[2 * i + 1] = z1; }
         for (int i = tid; i < LMAX; i += T) { reinterpret_cast<uint4*>(s_sorted)[2 * i] = z0; reinterpret_cast<uint4*>(s_sorted)[2 * i + 1] = z1; }
         for (int i = tid; i < ME; i += T) { reinterpret_cast<uint4*>(s_cs)[2 * i] = z0; reinterpret_cast<uint4*>(s_cs)[2 * i + 1] = z1; }
-        if (tid < 2) s_fail[tid] = LMAX;
     }
     __syncthreads();
     // the first sample of a scene is its first point (sampling_cuda_kernel.cu:39): "accepted" by nobody's list
@@ -190,7 +267,8 @@ fps_merge_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
     if (writer && lane == 0) idx[s_m] = s_n;
     const unsigned bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]);
     unsigned rslot0 = 0, rslot1 = 0, rbar0 = 0, rbar1 = 0;
-    if (C > 1) {
+    if (!GX && C > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
         if (tid == 0) {
             mbar_init(bar0, 1);
             mbar_init(bar1, 1);
@@ -215,7 +293,8 @@ fps_merge_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
     unsigned nb = 0u; int ni = -1; float nx = 0.f, ny = 0.f, nz = 0.f;   // argmax of st: the next entry to append
     float wmaxf = PLACEHOLDER_D2;   // this warp's real maximum (value of its list head)
     bool first = true;
-    unsigned long long n_rounds = 0;
+    bool stale = true;              // nxt no longer is the argmax of st (a foreign sample lowered that point)
+    unsigned long long n_rounds = 0, n_evals = 0;   // diagnostics
     int* out = idx + s_m;
     FpsEnt* const my_wl = s_wl + warp * WL;
 
@@ -239,24 +318,9 @@ fps_merge_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
             const bool own = valid && h.z == gw;
             unsigned tm = __ballot_sync(FULL, touch);
             const unsigned om = __ballot_sync(FULL, own);
-            const bool restart = first || (tm & ~om) != 0u;
-            while (tm) {
-                const int j = __ffs(tm) - 1;
-                tm &= tm - 1;
-                const float4 s = reinterpret_cast<const float4*>(&s_sorted[j])[1];
-#pragma unroll
-                for (int p = 0; p < P; p++) pt[p] = fminf(d2_ref(px[p], py[p], pz[p], s.x, s.y, s.z), pt[p]);
-            }
             const int c_own = __popc(om);
-            int fill = 0;
-            if (restart) {
-#pragma unroll
-                for (int p = 0; p < P; p++) st[p] = pt[p];
-                len = 0;
-                fps_warp_argmax<P>(st, warp_pts, lane, nb, ni, nx, ny, nz);
-                fill = D;
-            } else if (c_own) {
-                // its own head entries were taken (and nobody else reached in): the list shifts, st stays valid
+            // the merge took this warp's first c_own entries: the list shifts (st has them applied already)
+            if (c_own && !first) {
                 FpsEnt t;
                 const bool mv = lane + c_own <= len;
                 if (mv) t = ent_load(my_wl + lane + c_own);
@@ -268,14 +332,60 @@ fps_merge_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
                     ent_store(my_wl + lane, make_ent(0u, -1, 0.f, 0.f, 0.f, -1, false));
                 }
                 len -= c_own;
-                if (len == 0) fill = D;
                 __syncwarp();
             }
+            // lane i <= len watches entry i of the list (i == len: the terminal = nxt) against the foreign samples
+            float wx = 0.f, wy = 0.f, wz = 0.f, wv = -1.f;
+            if (lane <= len && !first) {
+                const FpsEnt* e = my_wl + lane;
+                const float4 wc = reinterpret_cast<const float4*>(e)[1];
+                wx = wc.x; wy = wc.y; wz = wc.z;
+                wv = (e->klo | e->khi) ? __uint_as_float(e->khi) : -1.f;   // EMPTY slots are never "lowered"
+            }
+            bool lowered = false;
+            const unsigned fm = tm & ~om;
+            while (tm) {
+                const int j = __ffs(tm) - 1;
+                const bool foreign = (fm >> j) & 1u;
+                tm &= tm - 1;
+                const float4 s = reinterpret_cast<const float4*>(&s_sorted[j])[1];
+                const unsigned rmask = (prune && !first) ? fps_row_mask<P>(rlo, rhi, s.x, s.y, s.z, wmaxf, lane)
+                                                         : (P < 32 ? (1u << P) - 1u : FULL);
+                if (foreign) {
+                    lowered = lowered || d2_ref(wx, wy, wz, s.x, s.y, s.z) < wv;
+                    POB_FPS_FOR_ROWS(rmask, {
+                        const float d = POB_FPS_D2(p, s.x, s.y, s.z);
+                        pt[p] = fminf(d, pt[p]);
+                        st[p] = fminf(d, st[p]);
+                    })
+                } else {
+                    POB_FPS_FOR_ROWS(rmask, { pt[p] = fminf(POB_FPS_D2(p, s.x, s.y, s.z), pt[p]); })
+                }
+                if (stats) n_evals += 32u * (unsigned)__popc(rmask);
+            }
+            const unsigned lm = __ballot_sync(FULL, lowered);
+            const bool restart = first || (lm & ((1u << len) - 1u)) != 0u;   // a pending entry was lowered: the list is void
+            stale = stale || ((lm >> len) & 1u);   // nxt itself was lowered: its value still bounds, recompute before use
+            int fill = 0;
+            if (restart) {
+#pragma unroll
+                for (int p = 0; p < P; p++) st[p] = pt[p];
+                len = 0;
+                stale = true;
+                fill = D;
+            } else {
+                fill = D - len;                                               // one local step per popped entry
+            }
             for (int d = 0; d < fill; d++) {
+                if (stale) { fps_warp_argmax<P>(st, warp_pts, lane, nb, ni, nx, ny, nz); stale = false; }
                 if (lane == 0) ent_store(my_wl + len, make_ent(nb, ni, nx, ny, nz, gw, !(nb == 0u && len > 0)));
                 len++;
-#pragma unroll
-                for (int p = 0; p < P; p++) st[p] = fminf(d2_ref(px[p], py[p], pz[p], nx, ny, nz), st[p]);
+                {   // nb is the maximum of st: rows farther than that from the new local sample cannot change
+                    const unsigned rmask = prune ? fps_row_mask<P>(rlo, rhi, nx, ny, nz, __uint_as_float(nb), lane)
+                                                 : (P < 32 ? (1u << P) - 1u : FULL);
+                    POB_FPS_FOR_ROWS(rmask, { st[p] = fminf(POB_FPS_D2(p, nx, ny, nz), st[p]); })
+                    if (stats) n_evals += 32u * (unsigned)__popc(rmask);
+                }
                 fps_warp_argmax<P>(st, warp_pts, lane, nb, ni, nx, ny, nz);
             }
             if (fill) {
@@ -312,7 +422,20 @@ fps_merge_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
         __syncthreads();   // (2) s_cs complete
 
         // ================= exchange =================
-        if (C > 1) {
+        if constexpr (GX) {
+            if (warp == 0) {   // message -> global, then arrive (release): the stores of the whole warp precede lane 0's fence
+                if (lane < 2 * ME) __stcg(reinterpret_cast<uint4*>(gmsg + ((size_t)par * C + rank) * ME) + lane, reinterpret_cast<const uint4*>(s_cs)[lane]);
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    atomicAdd(gcounter, 1u);
+                    const unsigned target = (unsigned)C * (unsigned)(round + 1);
+                    unsigned seen;
+                    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(gcounter) : "memory"); } while (seen < target);
+                }
+            }
+            __syncthreads();   // all G messages of this round are visible
+        } else if (C > 1) {
             if (warp == 0 && (lane & 15) < C) {
                 const unsigned rs = par ? rslot1 : rslot0, rb = par ? rbar1 : rbar0;
 #pragma unroll
@@ -328,8 +451,55 @@ fps_merge_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
             __syncthreads();
         }
 
-        // ================= phase D1: rank all NSLOT published entries, top LMAX -> s_sorted =================
-        {
+        // ================= phase D1: rank the published entries, top LMAX -> s_sorted =================
+        if constexpr (GX) {
+            const FpsEnt* gsrc = gmsg + (size_t)par * C * ME;
+            const int NS = C * ME;
+            for (int i = tid; i < NS; i += T) {
+                reinterpret_cast<uint4*>(s_all + i)[0] = __ldcg(reinterpret_cast<const uint4*>(gsrc + i));
+                reinterpret_cast<uint4*>(s_all + i)[1] = __ldcg(reinterpret_cast<const uint4*>(gsrc + i) + 1);
+            }
+            // T* = max over CTAs of the key of the first terminal of their (sorted) message: the walk ends there at the latest
+            unsigned long long tk = 0ull;
+            for (int c = tid; c < C; c += T) {
+                bool found = false;
+#pragma unroll
+                for (int e = 0; e < ME; e++) {
+                    const uint2 k2 = __ldcg(reinterpret_cast<const uint2*>(gsrc + c * ME + e));
+                    const unsigned long long k = ((unsigned long long)k2.y << 32) | k2.x;
+                    if (!found && !(k2.x & 1u)) { found = true; if (k > tk) tk = k; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(FULL, tk, o); tk = v > tk ? v : tk; }
+            if (lane == 0) s_red[warp] = tk;
+            __syncthreads();   // (a) s_all and the warp maxima are in
+            unsigned long long tstar = 0ull;
+#pragma unroll
+            for (int w = 0; w < NW; w++) tstar = s_red[w] > tstar ? s_red[w] : tstar;
+            for (int i0 = 0; i0 < NS; i0 += T) {   // uniform trip count
+                const int i = i0 + tid;
+                bool elig = false;
+                if (i < NS) { const unsigned long long k = ent_key(s_all + i); elig = (k & 1ull) && k > tstar; }
+                const unsigned em = __ballot_sync(FULL, elig);
+                int base = 0;
+                if (lane == 0 && em) base = atomicAdd(&s_cnt, __popc(em));
+                base = __shfl_sync(FULL, base, 0);
+                if (elig) s_cand[base + __popc(em & ((1u << lane) - 1u))] = (unsigned short)i;
+            }
+            __syncthreads();   // (b) candidates compacted
+            const int M = s_cnt;
+            for (int ci = warp; ci < M; ci += NW) {   // a warp per candidate: count the candidates above it
+                const FpsEnt* me = s_all + s_cand[ci];
+                const unsigned long long mk = ent_key(me);
+                int cnt = 0;
+                for (int j = lane; j < M; j += 32) cnt += ent_key(s_all + s_cand[j]) > mk ? 1 : 0;
+                const int tot = __reduce_add_sync(FULL, cnt);
+                if (tot < LMAX && lane < 2) reinterpret_cast<uint4*>(s_sorted + tot)[lane] = reinterpret_cast<const uint4*>(me)[lane];
+            }
+            if (M < LMAX && tid < 2)   // the walk stops after the last candidate: an EMPTY terminal
+                reinterpret_cast<uint4*>(s_sorted + M)[tid] = tid == 0 ? make_uint4(0u, 0u, 0xffffffffu, 0u) : make_uint4(0u, 0u, 0u, 0u);
+        } else {
             constexpr int EPW = NSLOT / NW;             // entries ranked by each warp
             constexpr int LPE = 32 / EPW;               // lanes per entry
             constexpr int CMPN = (NSLOT + LPE - 1) / LPE;
@@ -354,32 +524,77 @@ fps_merge_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, 
 
         // ================= phase D2: longest accepted prefix =================
         {
-            const int j = tid >> 3, i0 = tid & 7;
+            const int j = tid >> 3, i0 = tid & 7;       // thread (j, i0) tests entry j against entries i0, i0 + 8, i0 + 16, i0 + 24
             const int4 hj = reinterpret_cast<const int4*>(&s_sorted[j])[0];
             const float4 cj = reinterpret_cast<const float4*>(&s_sorted[j])[1];
             const float vj = __int_as_float(hj.y);
             bool fail = i0 == 0 && !(hj.x & 1);         // a terminal ends the walk
-            for (int i = i0; i < j; i += 8) {
+#pragma unroll
+            for (int t = 0; t < LMAX / 8; t++) {
+                const int i = i0 + 8 * t;
                 const int4 hi = reinterpret_cast<const int4*>(&s_sorted[i])[0];
                 const float4 ci = reinterpret_cast<const float4*>(&s_sorted[i])[1];
                 // exactly what the update computes for point j against sample i
-                if (hi.z != hj.z && d2_ref(cj.x, cj.y, cj.z, ci.x, ci.y, ci.z) < vj) fail = true;
+                fail = fail || (i < j && hi.z != hj.z && d2_ref(cj.x, cj.y, cj.z, ci.x, ci.y, ci.z) < vj);
             }
-            const unsigned fm = __ballot_sync(FULL, fail);
-            if (fm && lane == 0) atomicMin(&s_fail[par], (warp * 32 + __ffs(fm) - 1) >> 3);
+            const unsigned fm = __ballot_sync(FULL, fail);   // 8 lanes per j, four j per warp
+            if (lane == 0) {
+                const unsigned nib = ((fm & 0xffu) ? 1u : 0u) | ((fm & 0xff00u) ? 2u : 0u) | ((fm & 0xff0000u) ? 4u : 0u) |
+                                     ((fm & 0xff000000u) ? 8u : 0u);
+                s_failw[par][warp] = nib << (4 * warp);
+            }
         }
-        __syncthreads();   // (4) s_fail final
-        int Ln = s_fail[par];
-        if (tid == 0) s_fail[par ^ 1] = LMAX;
+        __syncthreads();   // (4) every warp's verdict on its four positions is in
+        int Ln;
+        {
+            const uint4 f0 = reinterpret_cast<const uint4*>(s_failw[par])[0], f1 = reinterpret_cast<const uint4*>(s_failw[par])[1];
+            const unsigned fmask = f0.x | f0.y | f0.z | f0.w | f1.x | f1.y | f1.z | f1.w;   // bit j: position j is not accepted
+            Ln = fmask ? __ffs(fmask) - 1 : LMAX;
+        }
+        if (GX && tid == 0) s_cnt = 0;   // next read is three barriers away
         if (Ln < 1) asm volatile("trap;");               // the top entry is always a real one: cannot happen
         if (Ln > total - emitted) Ln = total - emitted;
         if (writer && lane < Ln) out[emitted + lane] = 0x7fffffff - (int)(s_sorted[lane].klo >> 1);
         emitted += Ln;
         L = Ln;
     }
-    if (stats && tid == 0 && rank == 0) {   // diagnostics: rounds and samples per scene (mean chain = samples / rounds)
-        atomicAdd(stats, n_rounds);
-        atomicAdd(stats + 1, (unsigned long long)(total - 1));
+    if (stats) {   // diagnostics: rounds and samples per scene (mean chain = samples / rounds), point distances evaluated
+        if (tid == 0 && rank == 0) {
+            atomicAdd(stats, n_rounds);
+            atomicAdd(stats + 1, (unsigned long long)(total - 1));
+        }
+        if (lane == 0) atomicAdd(stats + 2, n_evals);
     }
-    if (C > 1) cluster.sync();  // nobody leaves while a peer may still be writing into its shared memory
+    if (!GX && C > 1) cg::this_cluster().sync();  // nobody leaves while a peer may still be writing into its shared memory
 }
+
+#define POB_FPS_MERGE_PARAMS                                                                                  \
+    const float *__restrict__ xyz, const int *__restrict__ offset, const int *__restrict__ new_offset,           \
+        const SceneGrid *__restrict__ scenes, const int *__restrict__ cell_start, const float4 *__restrict__ sorted, \
+        int *__restrict__ idx, unsigned long long *__restrict__ stats
+// register-resident points (small P: few registers anyway)
+template <int P, int T, int D, int KC>
+__global__ void __launch_bounds__(T, 1) fps_merge_kernel(POB_FPS_MERGE_PARAMS) {
+    fps_merge_body<P, T, D, KC, false, false>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats, 0, 0, nullptr, nullptr);
+}
+// shared-memory points, two CTAs per SM (<= 128 registers)
+template <int P, int T, int D, int KC>
+__global__ void __launch_bounds__(T, 2) fps_merge_sp_kernel(POB_FPS_MERGE_PARAMS) {
+    fps_merge_body<P, T, D, KC, false, true>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats, 0, 0, nullptr, nullptr);
+}
+// shared-memory points, one CTA per SM (P = 32: 64 registers of running minima alone)
+template <int P, int T, int D, int KC>
+__global__ void __launch_bounds__(T, 1) fps_merge_sp1_kernel(POB_FPS_MERGE_PARAMS) {
+    fps_merge_body<P, T, D, KC, false, true>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats, 0, 0, nullptr, nullptr);
+}
+
+// grid-wide form: cooperative launch of G CTAs for ONE scene; workspace = {counter (zeroed by the caller), gmsg[2][G][KC+1]}
+template <int P, int T, int D, int KC>
+__global__ void __launch_bounds__(T, 1)
+fps_merge_grid_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
+                      const SceneGrid* __restrict__ scenes, const int* __restrict__ cell_start,
+                      const float4* __restrict__ sorted, int* __restrict__ idx, unsigned long long* __restrict__ stats,
+                      int scene, int cap_points, FpsEnt* __restrict__ gmsg, unsigned* __restrict__ gcounter) {
+    fps_merge_body<P, T, D, KC, true, true>(xyz, offset, new_offset, scenes, cell_start, sorted, idx, stats, scene, cap_points, gmsg, gcounter);
+}
+#undef POB_FPS_MERGE_PARAMS

@@ -343,10 +343,12 @@ __global__ void __launch_bounds__(256) knn_grid_kernel(int64_t m, int k, int b, 
                                                        const int* __restrict__ cell_start,
                                                        const float4* __restrict__ sorted, int* __restrict__ idx_out,
                                                        float* __restrict__ dist_out, float* __restrict__ weight_out,
-                                                       int take_sqrt, int force_brute) {
+                                                       int take_sqrt, int force_brute,
+                                                       unsigned long long* __restrict__ stats) {
     const int lane = threadIdx.x & 31;
     const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= m) return;
+    unsigned evals = 0;   // diagnostics: candidates this query's warp evaluated a distance for
     const int s = segment_of(q, new_offset, b);
     const SceneGrid g = scenes[s];
     const float qx = __ldg(new_xyz + q * 3), qy = __ldg(new_xyz + q * 3 + 1), qz = __ldg(new_xyz + q * 3 + 2);
@@ -371,6 +373,7 @@ __global__ void __launch_bounds__(256) knn_grid_kernel(int64_t m, int k, int b, 
                                    __ldg(xyz + (int64_t)i * 3 + 2));
             topk_offer<KPL>(t, k, tau_d, tau_i, valid, cd, i, lane);
         }
+        evals += (unsigned)(g.end - g.start);
     } else {
         const int cx = cell_coord(qx, g.lox, g.inv_h, g.dx);
         const int cy = cell_coord(qy, g.loy, g.inv_h, g.dy);
@@ -399,6 +402,7 @@ __global__ void __launch_bounds__(256) knn_grid_kernel(int64_t m, int k, int b, 
                 }
                 const int total = __shfl_sync(FULL, incl, 31);
                 const int shift = beg - (incl - cnt);  // position = shift + ordinal, for ordinals of this row
+                evals += (unsigned)total;
                 for (int obase = 0; obase < total; obase += 32) {
                     const int o = obase + lane;
                     // smallest j with incl[j] > o
@@ -427,6 +431,7 @@ __global__ void __launch_bounds__(256) knn_grid_kernel(int64_t m, int k, int b, 
         }
     }
 
+    if (stats && lane == 0) atomicAdd(stats, (unsigned long long)evals);
     float recip[KPL], rsum = 0.f;
 #pragma unroll
     for (int r = 0; r < KPL; r++) {
@@ -724,11 +729,12 @@ POB_API int pob_knn_grid_build(int64_t n, int b, const float* xyz, const int* of
 
 static int knn_launch(int64_t m, int k, int b, const float* xyz, const float* new_xyz, const int* new_offset,
                       const SceneGrid* scenes, const int* cell_start, const float4* sorted, int* idx, float* dist,
-                      float* weight, int take_sqrt, int force_brute, cudaStream_t stream) {
+                      float* weight, int take_sqrt, int force_brute, cudaStream_t stream,
+                      unsigned long long* stats = nullptr) {
     const unsigned blocks = (unsigned)ceil_div(m, 8);
 #define POB_KNN_LAUNCH(KPL)                                                                                       \
     knn_grid_kernel<KPL><<<blocks, 256, 0, stream>>>(m, k, b, xyz, new_xyz, new_offset, scenes, cell_start, sorted, \
-                                                     idx, dist, weight, take_sqrt, force_brute)
+                                                     idx, dist, weight, take_sqrt, force_brute, stats)
     if (k <= 32) POB_KNN_LAUNCH(1);
     else if (k <= 64) POB_KNN_LAUNCH(2);
     else if (k <= 128) POB_KNN_LAUNCH(4);
@@ -740,7 +746,7 @@ static int knn_launch(int64_t m, int k, int b, const float* xyz, const float* ne
 
 POB_API int pob_knn_grid_query(int64_t m, int nsample, int64_t n, int b, const float* xyz, const float* new_xyz,
                                const int* new_offset, float cell_pts, const void* workspace, int* idx, float* dist,
-                               float* weight, int take_sqrt, cudaStream_t stream) {
+                               float* weight, int take_sqrt, void* stats_u64, cudaStream_t stream) {
     if (m < 0 || nsample < 1 || nsample > 256 || b < 1 || !workspace) return POB_ERR_BAD_ARG;
     if (m == 0) return 0;
     if (!new_xyz || !new_offset || !idx) return POB_ERR_BAD_ARG;
@@ -749,7 +755,7 @@ POB_API int pob_knn_grid_query(int64_t m, int nsample, int64_t n, int b, const f
     const char* ws = (const char*)workspace;
     return knn_launch(m, nsample, b, xyz, new_xyz, new_offset, (const SceneGrid*)(ws + L.off_scene),
                       (const int*)(ws + L.off_start), (const float4*)(ws + L.off_sorted), idx, dist, weight, take_sqrt,
-                      0, stream);
+                      0, stream, (unsigned long long*)stats_u64);
 }
 
 // Reference-shaped entry point: knn_query_cuda_launcher (knn_query_cuda_kernel.h:13) plus the
@@ -762,7 +768,7 @@ POB_API int pob_knn_query(int64_t m, int nsample, int64_t n, int b, const float*
     int rc = pob_knn_grid_build(n, b, xyz, offset, cell_pts, workspace, workspace_bytes, stream);
     if (rc) return rc;
     return pob_knn_grid_query(m, nsample, n, b, xyz, new_xyz, new_offset, cell_pts, workspace, idx, dist, nullptr,
-                              take_sqrt, stream);
+                              take_sqrt, nullptr, stream);
 }
 
 // Exhaustive variant (same key, same d2): every query scans its whole scene.  Needs only the

@@ -171,6 +171,9 @@ _GRID_CACHE_SIZE = int(os.environ.get("POINTOPS_B200_GRID_CACHE", "8"))
 _KNN_CACHE_SIZE = int(os.environ.get("POINTOPS_B200_KNN_CACHE", "8"))
 
 
+KNN_STATS = None   # diagnostics (bench.py): a device int64 tensor every grid query adds its evaluated-candidate count to
+
+
 class NeighbourGrid:
     """Device-resident uniform grid over (xyz, offset): the workspace pob_knn_grid_build fills."""
 
@@ -183,7 +186,8 @@ class NeighbourGrid:
         _lib.run("pob_knn_grid_build", self.n, self.b, _lib.ptr(xyz), _lib.ptr(offset), self.cell_pts,
                  _lib.ptr(self.workspace), nbytes, _lib.current_stream(xyz.device), alg_bytes=28 * self.n)
 
-    def query(self, nsample: int, new_xyz: torch.Tensor, new_offset: torch.Tensor, want_dist=True, want_weight=False):
+    def query(self, nsample: int, new_xyz: torch.Tensor, new_offset: torch.Tensor, want_dist=True, want_weight=False,
+              stats: Optional[torch.Tensor] = None):
         lib = _lib.load()
         m = int(new_xyz.shape[0])
         dev = new_xyz.device
@@ -193,7 +197,7 @@ class NeighbourGrid:
         outs = 1 + (dist is not None) + (weight is not None)
         _lib.run("pob_knn_grid_query", m, int(nsample), self.n, self.b, _lib.ptr(self.xyz), _lib.ptr(new_xyz),
                  _lib.ptr(new_offset), self.cell_pts, _lib.ptr(self.workspace), _lib.ptr(idx), _lib.ptr(dist),
-                 _lib.ptr(weight), 1, _lib.current_stream(dev),
+                 _lib.ptr(weight), 1, _lib.ptr(stats if stats is not None else KNN_STATS), _lib.current_stream(dev),
                  alg_bytes=12 * self.n + 12 * m + 4 * outs * nsample * m,
                  alg_flops=8 * m * max(self.n // max(self.b, 1), 1))             # brute-force equivalent
         return idx, dist, weight

@@ -15,6 +15,7 @@ CLUSTER_HINT = int(os.environ.get("POINTOPS_B200_FPS_CLUSTER", "0"))   # 0 = the
 VARIANTS = {"auto": 0, "merge": 1, "chain": 2, "single": 3}
 VARIANT = VARIANTS[os.environ.get("POINTOPS_B200_FPS", "auto")]
 RESIDENT_MAX = 131072   # points per scene the cluster-resident kernels hold in registers
+STATS = None            # diagnostics (bench.py): device int64[4] every launch accumulates {rounds, samples, distances, -} into
 
 
 def fps_launch(xyz, offset, new_offset, offset_host, new_offset_host, variant=None, stats=None, cluster_hint=None):
@@ -39,7 +40,7 @@ def fps_launch(xyz, offset, new_offset, offset_host, new_offset_host, variant=No
                  _lib.ptr(tmp), _lib.ptr(idx), CLUSTER_HINT if cluster_hint is None else int(cluster_hint),
                  _lib.ptr(grid.workspace if grid else None), xyz.shape[0], grid.cell_pts if grid else 0.0,
                  VARIANT if variant is None else VARIANTS[variant] if isinstance(variant, str) else int(variant),
-                 _lib.ptr(stats), _lib.current_stream(xyz.device),
+                 _lib.ptr(stats if stats is not None else STATS), _lib.current_stream(xyz.device),
                  alg_bytes=12 * xyz.shape[0] + 4 * m, alg_flops=flops)
     return idx
 

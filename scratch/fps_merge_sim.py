@@ -21,6 +21,7 @@ KC = int(sys.argv[5]) if len(sys.argv) > 5 else 0      # entries a CTA (8 warps)
 MLIM = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 LMAX = int(sys.argv[7]) if len(sys.argv) > 7 else 32
 LAZY = int(sys.argv[8]) if len(sys.argv) > 8 else 0   # 1: a clean warp refills only when its list is empty
+KEEP = int(os.environ.get("KEEP", "0"))   # 1: a foreign sample is applied to spec too; restart only if it lowers a pending entry
 m = n // 4
 if MLIM:
     m = min(m, MLIM)
@@ -30,6 +31,17 @@ h = max((Lb.prod() / (n / 2)) ** (1 / 3), 1e-3)
 cell = np.floor((xyz - xyz.min(0)) / h).astype(np.int64)
 dd = cell.max(0) + 1
 key = (cell[:, 2] * dd[1] + cell[:, 1]) * dd[0] + cell[:, 0]
+ORDER = os.environ.get("ORDER", "row")
+if ORDER.startswith("morton"):
+    B = int(ORDER[6:] or 2)            # block edge in cells
+    blk = cell // B
+    def spread(v):
+        out = np.zeros_like(v)
+        for i in range(10):
+            out |= ((v >> i) & 1) << (3 * i)
+        return out
+    code = spread(blk[:, 0]) | (spread(blk[:, 1]) << 1) | (spread(blk[:, 2]) << 2)
+    key = code * (dd.prod() + 1) + key     # Morton over blocks, row-major (z, y, x) inside a block
 order = np.argsort(key, kind="stable")
 pts = xyz[order]
 gid = order
@@ -61,7 +73,16 @@ term = np.zeros(W)         # terminal bound
 wmax = np.full(W, 1e10)
 
 
+steps_tot = 0
+
+
+step_log = {}
+
+
 def local_step(w):
+    global steps_tot
+    steps_tot += 1
+    step_log[w] = step_log.get(w, 0) + 1
     a, b = bounds[w]
     if b <= a:
         term[w] = 0.0
@@ -138,6 +159,8 @@ while len(out) < m:
     out += [e[1] for e in acc]
     # ---- apply ----
     dirty = set()
+    napply = np.zeros(W, dtype=np.int64)
+    nsteps0 = steps_tot
     for e in acc:
         p = pts[e[2]]
         ex = np.maximum(np.maximum(lo - p, p - hi), 0.0)
@@ -148,8 +171,14 @@ while len(out) < m:
                 continue
             np.minimum(tmp[a:b], d2(pts[a:b], p), out=tmp[a:b])
             if w != e[3]:
-                dirty.add(w)
+                if KEEP:
+                    np.minimum(spec[w], d2(pts[a:b], p), out=spec[w])
+                    if any(d2(pts[le[2]], p) < le[0] for le in lists[w]):
+                        dirty.add(w)
+                else:
+                    dirty.add(w)
             touched_tot += 1
+            napply[w] += 1
         w = e[3]
         assert lists[w][0][2] == e[2]
         lists[w].pop(0)
@@ -158,6 +187,7 @@ while len(out) < m:
         if b > a:
             wmax[w] = tmp[a:b].max()
     mx = 0
+    restarts_tot = globals().get("restarts_tot", 0) + len(dirty)
     for w in range(W):
         if w in dirty:
             restart(w, D0); mx = max(mx, D0)
@@ -168,5 +198,14 @@ while len(out) < m:
                     local_step(w)
                 mx = max(mx, 1)
     crit_steps += mx
+    stepw = np.zeros(W, dtype=np.int64)
+    for w in range(W):
+        stepw[w] = step_log.get(w, 0)
+    step_log.clear()
+    cost = napply * 210 + stepw * 480 + np.array([300 if w in dirty else 0 for w in range(W)])
+    cost_max_sum = globals().get("cost_max_sum", 0) + cost.max()
+    cost_mean_sum = globals().get("cost_mean_sum", 0) + cost.mean()
+    apply_max_sum = globals().get("apply_max_sum", 0) + napply.max()
 print(f"n={n} W={W} D0={D0} DMAX={DMAX} KC={KC} LMAX={LMAX}: identical={out == ref[:len(out)]} rounds={rounds} samples={len(out)-1} "
-      f"mean chain={(len(out) - 1) / rounds:.2f} touched/round={touched_tot / rounds:.1f} stops={stop_reason}")
+      f"cost max/mean per round={cost_max_sum / rounds:.0f}/{cost_mean_sum / rounds:.0f} cyc, max applies/warp={apply_max_sum / rounds:.1f} "
+      f"mean chain={(len(out) - 1) / rounds:.2f} restarts/round={restarts_tot / rounds:.1f} steps/round={steps_tot / rounds:.1f} touched/round={touched_tot / rounds:.1f} stops={stop_reason}")

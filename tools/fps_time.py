@@ -28,7 +28,7 @@ for n in [int(v) for v in args.sizes.split(",")]:
     for v in args.variants.split(","):
         for cl in [int(c) for c in args.clusters.split(",")]:
             out = torch.empty(m, dtype=torch.int32, device=dev)
-            stats = torch.zeros(2, dtype=torch.int64, device=dev)
+            stats = torch.zeros(4, dtype=torch.int64, device=dev)
             best = 1e9
             for r in range(args.reps):
                 stats.zero_()
@@ -45,9 +45,9 @@ for n in [int(v) for v in args.sizes.split(",")]:
             st = stats.tolist()
             chain = st[1] / max(st[0], 1)
             row = dict(n=n, m=m, variant=v, cluster=cl, ms=best, ns_per_sample=best * 1e6 / m, rounds=st[0], samples_per_round=chain,
-                       ns_per_round=best * 1e6 / max(st[0], 1), same_as_first=bool(torch.equal(out, ref)))
+                       ns_per_round=best * 1e6 / max(st[0], 1), d2_evals=st[2], same_as_first=bool(torch.equal(out, ref)))
             rows.append(row)
             print(f"n={n:7d} m={m:6d} {v:6s} C={cl:2d}: {best:8.3f} ms {row['ns_per_sample']:7.1f} ns/sample rounds={st[0]:6d} "
-                  f"chain={chain:5.2f} {row['ns_per_round']:7.1f} ns/round same={row['same_as_first']}", flush=True)
+                  f"chain={chain:5.2f} {row['ns_per_round']:7.1f} ns/round evals/sample={st[2] / max(st[1], 1):7.0f} same={row['same_as_first']}", flush=True)
 if args.json:
     json.dump(rows, open(args.json, "w"), indent=1)
