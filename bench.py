@@ -589,20 +589,37 @@ def cfg5_sharded_knn(dev, rank, world, dist):
             msN, got = timed(sharded)
             msL, _ = timed(local_only)
             equal = bool(torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1]))
-            eq = torch.tensor([1 if equal else 0], device=dev)
+            fused = {}
+            try:   # the same step with the all-gather fused into the query kernel (P2P stores into every rank's result)
+                def fused_fn():
+                    C.clear_caches()
+                    return sharding.sharded_knn_query_fused(k, xyz, off, off_host)
+                msF, gotF = timed(fused_fn)
+                equal_f = bool(torch.equal(ref[0], gotF[0]) and torch.equal(ref[1], gotF[1]))
+                fused = {"fused_ms": msF, "fused_speedup": ms1 / msF, "fused_queries_per_sec": n / msF * 1e3, "_eq": equal_f}
+                del gotF
+            except Exception as e:   # noqa: BLE001
+                fused = {"fused_error": f"{type(e).__name__}: {e}"[:200], "_eq": True}
+            eq = torch.tensor([1 if equal else 0, 1 if fused.pop("_eq") else 0], device=dev)
             if world > 1:
                 dist.all_reduce(eq, op=dist.ReduceOp.MIN)
-            rows.append({"n": n, "k": k, "n_gpus": world, "one_gpu_ms": ms1, "sharded_ms": msN, "local_kernel_ms": msL,
-                         "all_gather_and_assembly_ms": max(msN - msL, 0.0), "speedup": ms1 / msN,
-                         "queries_per_sec": n / msN * 1e3, "equal_to_single_gpu": bool(int(eq.item())),
-                         "gathered_MB": 8 * n * k / 1e6})
+            row = {"n": n, "k": k, "n_gpus": world, "one_gpu_ms": ms1, "sharded_ms": msN, "local_kernel_ms": msL,
+                   "all_gather_and_assembly_ms": max(msN - msL, 0.0), "speedup": ms1 / msN,
+                   "queries_per_sec": n / msN * 1e3, "equal_to_single_gpu": bool(int(eq[0].item())),
+                   "gathered_MB": 8 * n * k / 1e6}
+            row.update(fused)
+            if "fused_ms" in fused:
+                row["fused_equal_to_single_gpu"] = bool(int(eq[1].item()))
+            rows.append(row)
             del ref, got
         del xyz, off
         torch.cuda.empty_cache()
     C.clear_caches()
     return {"rows": rows, "what": "grid build (replicated on every rank) + query of the rank's contiguous slice of the queries + "
                                   "NCCL all-gather of idx (i32) and dist (f32) + assembly into the (n, k) result on every rank; "
-                                  "CUDA events, median of 5, max over ranks"}
+                                  "fused_*: the same with the all-gather done by the query kernel itself (P2P stores into every "
+                                  "rank's symmetric result buffer over NVLink, one device-side barrier); CUDA events, median of 5, "
+                                  "max over ranks"}
 
 
 # ------------------------------------------------------------------------------- B200 arm --
@@ -709,13 +726,20 @@ def main():
     # ---- how often the K-step schedule is repeated inside one timed window: K steps of a 12-deep pipeline are
     #      mostly fill and drain (47 ms at K = 20), so a window repeats the schedule until it lasts >= min_window_s;
     #      every rank uses the same count (max over ranks of the calibration) ----
-    calib_ms, _ = timed_window(resident, max(K, depth + 2))
-    est_step = calib_ms / max(K, depth + 2)
-    t = torch.tensor([est_step], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    est_step = float(t[0])
+    def agree(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    n_cal = max(K, 4 * depth)
+    est_step = agree(timed_window(resident, n_cal)[0] / n_cal)
     repeats = max(1, int(-(-args.min_window_s * 1e3 // (K * est_step))))
+    for _ in range(3):   # the calibration run is mostly pipeline fill: check a full window and lengthen it if it came out short
+        got = agree(timed_window(resident, K * repeats)[0])
+        if got >= 0.95 * args.min_window_s * 1e3:
+            break
+        repeats = max(repeats + 1, int(-(-repeats * args.min_window_s * 1e3 * 1.05 // got)))
     M = K * repeats
     n_win = max(1, args.windows)
 

@@ -63,6 +63,15 @@ int pob_knn_grid_build(int64_t n, int b, const float* xyz, const int* offset, fl
 int pob_knn_grid_query(int64_t m, int nsample, int64_t n, int b, const float* xyz, const float* new_xyz,
                        const int* new_offset, float cell_pts, const void* workspace, int* idx, float* dist,
                        float* weight, int take_sqrt, void* stats_u64, cudaStream_t stream);
+/* Query a built grid and store every result row into the (n_total, nsample) result buffers of ALL ranks of a
+ * multi-GPU job (the large-scene form of SURVEY.md 8e: queries sharded, reference set replicated): peer_idx /
+ * peer_dist are HOST arrays of npeers <= 16 device pointers into peer-mapped memory (the caller's own buffer among
+ * them; peer_dist may be NULL), row_base = row of this rank's first query.  Replaces "local kernel + NCCL
+ * all-gather" by P2P stores issued from the query kernel itself.  The caller synchronises the ranks afterwards.  */
+int pob_knn_grid_query_scatter(int64_t m, int nsample, int64_t n, int b, const float* xyz, const float* new_xyz,
+                               const int* new_offset, float cell_pts, const void* workspace, int64_t row_base,
+                               int npeers, int* const* peer_idx, float* const* peer_dist, int take_sqrt,
+                               cudaStream_t stream);
 /* Build + query in one call, cell_pts = 2; workspace >= pob_knn_grid_workspace_bytes(n, b, 2). */
 int pob_knn_query(int64_t m, int nsample, int64_t n, int b, const float* xyz, const float* new_xyz,
                   const int* offset, const int* new_offset, int* idx, float* dist, int take_sqrt,

@@ -13,6 +13,9 @@ backend (reference_modules):
              (oracle/_ref/libpointops_ref.so, compiled unmodified) on CUDA tensors: the GPU "before";
   "product"  ``pointops`` = this repo's drop-in package: the unmodified callers
              (point_transformer_seg.py, pt_v1.py, max_probability_v1m1_base.py) on the new kernels.
+  "shim"     the reference's functions package over a COMPILED ``pointops._C`` replacement
+             (integration/pointops_C_shim.cpp: pybind shims with the reference's signatures over the C ABI
+             of include/pointops_b200.h) -- the binding a maintainer would add to keep ``pointops._C``.
 
 The reference package ``libs/pointops/functions`` is imported *unmodified* from
 where it lies, under the name ``pointops``; the CUDA extension it binds
@@ -207,7 +210,7 @@ def reference_modules(backend: str = "oracle"):
     if REF_ROOT is None:
         raise RuntimeError("reference python files found neither at /root/reference nor under baseline/_ref "
                            "(python -m oracle.stage_reference stages them where the reference is mounted)")
-    if backend not in ("oracle", "refgpu", "product"):
+    if backend not in ("oracle", "refgpu", "product", "shim"):
         raise ValueError(backend)
     saved_modules = {k: v for k, v in sys.modules.items() if k == "pointops" or k.startswith("pointops.")
                      or k == "pointcept" or k.startswith("pointcept.")}
@@ -234,7 +237,13 @@ def reference_modules(backend: str = "oracle"):
                                                           submodule_search_locations=[fdir])
             pointops = importlib.util.module_from_spec(spec)
             sys.modules["pointops"] = pointops
-            sys.modules["pointops._C"] = _make_C_stub() if backend == "oracle" else _make_C_stub_refgpu()
+            if backend == "shim":
+                if REPO_ROOT not in sys.path:
+                    sys.path.insert(0, REPO_ROOT)
+                from integration import build_shim
+                sys.modules["pointops._C"] = build_shim.load()
+            else:
+                sys.modules["pointops._C"] = _make_C_stub() if backend == "oracle" else _make_C_stub_refgpu()
             spec.loader.exec_module(pointops)
 
         # registry stubs for pointcept.models.builder / pointcept.recognizers.builder

@@ -27,6 +27,7 @@ SIGNATURES = {
     "pob_knn_grid_workspace_bytes": (Z, [L, I, F]),
     "pob_knn_grid_build": (I, [L, I, P, P, F, P, Z, P]),
     "pob_knn_grid_query": (I, [L, I, L, I, P, P, P, F, P, P, P, P, I, P, P]),
+    "pob_knn_grid_query_scatter": (I, [L, I, L, I, P, P, P, F, P, L, I, P, P, I, P]),
     "pob_knn_query": (I, [L, I, L, I, P, P, P, P, P, P, I, P, Z, P]),
     "pob_knn_query_bruteforce": (I, [L, I, I, P, P, P, P, P, P, I, P, Z, P]),
     "pob_ball_query": (I, [L, I, F, F, L, I, P, P, P, F, P, P, P, P, P]),

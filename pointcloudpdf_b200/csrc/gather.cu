@@ -540,6 +540,30 @@ static bool launch_reduce_fast(int lpr, int ns, int64_t n, const float* gout, fl
     return true;
 }
 
+static bool launch_sub_fwd_fast(int lpr, int ns, int64_t n, const float* in1, const float* in2, const int* idx, float* out,
+                                cudaStream_t stream) {
+    if (!ns_tiled(lpr, ns)) return false;
+#define M(L) { if (ns == 8) { if constexpr (tile_ok<L, 8>()) { constexpr int U = ((8 / (32 / L)) > 8) ? 8 / (32 / L) : 8; \
+            subtraction_fwd_fast<L, 8><<<fast_grid(ceil_div(n, (U * (32 / L)) / 8)), FAST_THREADS, 0, stream>>>(n, (const float4*)in1, (const float4*)in2, idx, (float4*)out); } } \
+        else { if constexpr (tile_ok<L, 16>()) { constexpr int U = ((16 / (32 / L)) > 8) ? 16 / (32 / L) : 8; \
+            subtraction_fwd_fast<L, 16><<<fast_grid(ceil_div(n, (U * (32 / L)) / 16)), FAST_THREADS, 0, stream>>>(n, (const float4*)in1, (const float4*)in2, idx, (float4*)out); } } }
+    POB_LPR_SWITCH(lpr, M)
+#undef M
+    return true;
+}
+
+static bool launch_sub_bwd_fast(int lpr, int ns, int64_t n, const float* gout, const int* idx, float* g1, float* g2,
+                                cudaStream_t stream) {
+    if (!ns_tiled(lpr, ns)) return false;
+#define M(L) { if (ns == 8) { if constexpr (tile_ok<L, 8>()) { constexpr int U = ((8 / (32 / L)) > 8) ? 8 / (32 / L) : 8; \
+            subtraction_bwd_fast<L, 8><<<fast_grid(ceil_div(n, (U * (32 / L)) / 8)), FAST_THREADS, 0, stream>>>(n, (const float4*)gout, idx, (float4*)g1, (float4*)g2); } } \
+        else { if constexpr (tile_ok<L, 16>()) { constexpr int U = ((16 / (32 / L)) > 8) ? 16 / (32 / L) : 8; \
+            subtraction_bwd_fast<L, 16><<<fast_grid(ceil_div(n, (U * (32 / L)) / 16)), FAST_THREADS, 0, stream>>>(n, (const float4*)gout, idx, (float4*)g1, (float4*)g2); } } }
+    POB_LPR_SWITCH(lpr, M)
+#undef M
+    return true;
+}
+
 // pipelined (bulk-async) aggregation over the full tiles; returns the number of points it covered
 template <int L, int NS>
 static int64_t launch_agg_fwd_pipe(int64_t n, int wvec, const float* in, const float* pos, const float* w,
@@ -624,7 +648,7 @@ static int launch_group_xyz_fwd_fast(int lpr, int64_t m, int ns, const T* feat, 
                                      const int* idx, float* out, cudaStream_t stream) {
     const int per = ns * (4 * lpr + 3);
     const size_t smem = sizeof(float) * (size_t)((per + 3) & ~3) * (FAST_THREADS / 32);
-    if (smem > 200 * 1024) return -1;
+    if (smem > 200 * 1024 || ns > 32) return -1;   // the kernel keeps one neighbour index per lane
 #define M(L) { auto kern = group_xyz_fwd_fast<T, L>; \
         if (smem > 48 * 1024) POB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<fast_grid(m), FAST_THREADS, smem, stream>>>(m, ns, feat, xyz, new_xyz, idx, out); }
@@ -704,7 +728,8 @@ POB_API int pob_subtraction_forward(int64_t n, int nsample, int c, const float* 
     if (!input1 || !input2 || !idx || !output) return POB_ERR_BAD_ARG;
     const RowTile t = row_tile(c);
     if (aligned16(input1) && aligned16(input2) && aligned16(output) &&
-        launch_gather_fast<float, true, false>(lpr_of(c), rows, nsample, input2, input1, idx, output, stream)) {
+        (launch_sub_fwd_fast(lpr_of(c), nsample, n, input1, input2, idx, output, stream) ||
+         launch_gather_fast<float, true, false>(lpr_of(c), rows, nsample, input2, input1, idx, output, stream))) {
     } else if (t.ok && aligned16(input1) && aligned16(input2) && aligned16(output)) {
         gather_rows_kernel<true><<<warp_grid(ceil_div(rows, t.spar * 4)), GATHER_THREADS, 0, stream>>>(
             rows, nsample, t, input2, input1, idx, output);
@@ -725,6 +750,11 @@ POB_API int pob_subtraction_backward(int64_t n, int nsample, int c, const int* i
     if (rows == 0) return 0;
     if (!idx || !grad_output || !grad_input1 || !grad_input2) return POB_ERR_BAD_ARG;
     const RowTile t = row_tile(c);
+    if (t.ok && aligned16(grad_output) && aligned16(grad_input1) && aligned16(grad_input2) &&
+        launch_sub_bwd_fast(lpr_of(c), nsample, n, grad_output, idx, grad_input1, grad_input2, stream)) {
+        pob_count_launches(1);
+        POB_RETURN_LAST_ERROR();
+    }
     if (t.ok && aligned16(grad_output) && aligned16(grad_input1) && aligned16(grad_input2)) {
         if (!launch_reduce_fast(lpr_of(c), nsample, n, grad_output, grad_input1, stream))
             reduce_neighbours_kernel<<<warp_grid(n), GATHER_THREADS, 0, stream>>>(n, nsample, t, grad_output, grad_input1);

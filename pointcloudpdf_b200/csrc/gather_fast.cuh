@@ -190,33 +190,43 @@ group_xyz_fwd_fast(int64_t m, int ns, const T* __restrict__ feat, const float* _
     const int64_t nwarps = ((int64_t)gridDim.x * FAST_THREADS) >> 5;
     for (int64_t q = warp; q < m; q += nwarps) {
         const int* iq = idx + q * ns;
-        // features: SPAR rows per pass, one 16-byte gather per lane
-        for (int s0 = 0; s0 < ns; s0 += SPAR) {
-            const int s = s0 + sub;
-            if (s < ns) {
-                const int src = __ldg(iq + s);
-                const float4 v = src >= 0 ? Vec4Load<T>::ld(feat, (int64_t)src * LPR + cl) : zero4();
-                float* t = tile + s * W + 3 + 4 * cl;
-                t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+        // one index load per neighbour (lane s holds idx[q, s]); the feature passes fetch theirs by shuffle
+        const int my_src = lane < ns ? __ldg(iq + lane) : -1;
+        const float qx = __ldg(new_xyz + q * 3), qy = __ldg(new_xyz + q * 3 + 1), qz = __ldg(new_xyz + q * 3 + 2);
+        float dx = 0.f, dy = 0.f, dz = 0.f;
+        if (my_src >= 0) {
+            dx = __fsub_rn(__ldg(xyz + (int64_t)my_src * 3), qx);
+            dy = __fsub_rn(__ldg(xyz + (int64_t)my_src * 3 + 1), qy);
+            dz = __fsub_rn(__ldg(xyz + (int64_t)my_src * 3 + 2), qz);
+        }
+        // the gathers of up to CH passes are issued before anything is stored (independent 16-byte loads per lane)
+        constexpr int CH = (32 / SPAR) < 8 ? (32 / SPAR) : 8;      // ns <= 32 here (the launcher checks)
+        for (int s0 = 0; s0 < ns; s0 += CH * SPAR) {
+            float4 v[CH];
+#pragma unroll
+            for (int ps = 0; ps < CH; ps++) {
+                const int s = s0 + ps * SPAR + sub;
+                const int src = __shfl_sync(FULL, my_src, s & 31);
+                v[ps] = (s < ns && src >= 0) ? Vec4Load<T>::ld(feat, (int64_t)src * LPR + cl) : zero4();
+            }
+#pragma unroll
+            for (int ps = 0; ps < CH; ps++) {
+                const int s = s0 + ps * SPAR + sub;
+                if (s < ns) {
+                    float* t = tile + s * W + 3 + 4 * cl;
+                    t[0] = v[ps].x; t[1] = v[ps].y; t[2] = v[ps].z; t[3] = v[ps].w;
+                }
             }
         }
-        // relative coordinates: one neighbour per lane
-        for (int s = lane; s < ns; s += 32) {
-            const int src = __ldg(iq + s);
-            float dx = 0.f, dy = 0.f, dz = 0.f;
-            if (src >= 0) {
-                dx = __fsub_rn(__ldg(xyz + (int64_t)src * 3), __ldg(new_xyz + q * 3));
-                dy = __fsub_rn(__ldg(xyz + (int64_t)src * 3 + 1), __ldg(new_xyz + q * 3 + 1));
-                dz = __fsub_rn(__ldg(xyz + (int64_t)src * 3 + 2), __ldg(new_xyz + q * 3 + 2));
-            }
-            tile[s * W] = dx; tile[s * W + 1] = dy; tile[s * W + 2] = dz;
-        }
+        if (lane < ns) { tile[lane * W] = dx; tile[lane * W + 1] = dy; tile[lane * W + 2] = dz; }
         __syncwarp();
         float* o = out + q * per;
         if ((per & 3) == 0) {   // q*per*4 bytes is then a multiple of 16
             const float4* t4 = reinterpret_cast<const float4*>(tile);
             float4* o4 = reinterpret_cast<float4*>(o);
-            for (int v = lane; v < per / 4; v += 32) stcs4(o4 + v, t4[v]);
+            const int nv = per / 4;
+#pragma unroll 4
+            for (int vv = lane; vv < nv; vv += 32) stcs4(o4 + vv, t4[vv]);
         } else {
             for (int f = lane; f < per; f += 32) __stcs(o + f, tile[f]);
         }
@@ -286,6 +296,87 @@ scatter_rows_fast(int64_t rows, float sign, const float4* __restrict__ gout, con
 #pragma unroll
         for (int u = 0; u < U; u++)
             if (dst[u] >= 0) red_add4(gin + (int64_t)dst[u] * LPR + cl, scale4(v[u], sign));
+    }
+}
+
+// out[n, s, :] = in1[n, :] - in2[idx[n, s], :]          (subtraction forward, whole points per tile)
+// The row-tiled form above (SUB) reloads in1 for every row and holds two float4 per row slot: 75 registers,
+// 3 CTAs per SM, 32 % of the warps active and twice the time of the plain gather (ncu, profiles/r02_ops_ncu.md).
+// Here a tile is PPT whole points: in1 is read once per point, and the launch bound keeps 5 CTAs per SM.
+template <int LPR, int NS>
+__global__ void __launch_bounds__(FAST_THREADS, 5)
+subtraction_fwd_fast(int64_t n, const float4* __restrict__ in1, const float4* __restrict__ in2, const int* __restrict__ idx,
+                     float4* __restrict__ out) {
+    constexpr int SPAR = 32 / LPR;
+    constexpr int U = (NS / SPAR > 8) ? NS / SPAR : 8;
+    constexpr int R = U * SPAR, PPT = R / NS, UPP = U / PPT;
+    static_assert(NS % SPAR == 0 && R % NS == 0, "tile must hold whole points");
+    const int lane = threadIdx.x & 31, sub = lane / LPR, cl = lane % LPR;
+    const int64_t warp = ((int64_t)blockIdx.x * FAST_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * FAST_THREADS) >> 5;
+    const int64_t ntiles = (n + PPT - 1) / PPT;
+    for (int64_t tile = warp; tile < ntiles; tile += nwarps) {
+        const int64_t p0 = tile * PPT, row0 = p0 * NS;
+        const bool full = p0 + PPT <= n;
+        const int* ip = idx + row0 + sub;
+        float4* op = out + row0 * LPR + lane;
+        int src[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) src[u] = (full || p0 + u / UPP < n) ? __ldg(ip + u * SPAR) : -1;
+        float4 a1[PPT];
+#pragma unroll
+        for (int q = 0; q < PPT; q++) a1[q] = (full || p0 + q < n) ? ldg4(in1 + (p0 + q) * LPR + cl) : zero4();
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (full || p0 + u / UPP < n) {
+                const float4 g = src[u] >= 0 ? ldg4(in2 + (int64_t)src[u] * LPR + cl) : zero4();
+                stcs4(op + u * 32, sub4(a1[u / UPP], g));
+            }
+        }
+    }
+}
+
+// g1[n, :] = sum_s gout[n, s, :] ; g2[idx[n, s], :] -= gout[n, s, :]     (subtraction backward, ONE pass over gout:
+// the reduction for input1 and the vector-atomic scatter for input2 share the streamed tile)
+template <int LPR, int NS>
+__global__ void __launch_bounds__(FAST_THREADS)
+subtraction_bwd_fast(int64_t n, const float4* __restrict__ gout, const int* __restrict__ idx, float4* __restrict__ g1,
+                     float4* __restrict__ g2) {
+    constexpr int SPAR = 32 / LPR;
+    constexpr int U = (NS / SPAR > 8) ? NS / SPAR : 8;
+    constexpr int R = U * SPAR, PPT = R / NS, UPP = U / PPT;
+    static_assert(NS % SPAR == 0 && R % NS == 0, "tile must hold whole points");
+    const int lane = threadIdx.x & 31, sub = lane / LPR, cl = lane % LPR;
+    const int64_t warp = ((int64_t)blockIdx.x * FAST_THREADS + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * FAST_THREADS) >> 5;
+    const int64_t ntiles = (n + PPT - 1) / PPT;
+    for (int64_t tile = warp; tile < ntiles; tile += nwarps) {
+        const int64_t p0 = tile * PPT, row0 = p0 * NS;
+        const bool full = p0 + PPT <= n;
+        const float4* gp = gout + row0 * LPR + lane;
+        const int* ip = idx + row0 + sub;
+        float4 b[U];
+        int dst[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool ok = full || p0 + u / UPP < n;
+            dst[u] = ok ? __ldg(ip + u * SPAR) : -1;
+            b[u] = ok ? ldcs4(gp + u * 32) : zero4();
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (dst[u] >= 0) red_add4(g2 + (int64_t)dst[u] * LPR + cl, scale4(b[u], -1.f));
+        float4 acc[PPT];
+#pragma unroll
+        for (int q = 0; q < PPT; q++) acc[q] = zero4();
+#pragma unroll
+        for (int u = 0; u < U; u++) acc[u / UPP] = add4(acc[u / UPP], b[u]);
+#pragma unroll
+        for (int q = 0; q < PPT; q++) {
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) acc[q] = add4(acc[q], xor4(acc[q], o));
+            if (sub == q % SPAR && (full || p0 + q < n)) g1[(p0 + q) * LPR + cl] = acc[q];
+        }
     }
 }
 

@@ -335,6 +335,19 @@ __device__ __forceinline__ float bound2(int R, float h) {
     return r * r * 0.9999f;
 }
 
+// Fused "query -> all-gather": when npeers > 0 every result row is stored straight into the result buffers of ALL
+// ranks (peer-mapped device memory: NVLink / NVSwitch P2P stores) at row row_base + q, instead of into a local
+// shard that an NCCL all-gather would then copy around.  The stores of one warp are a contiguous k * 4-byte row per
+// peer; they drain over NVLink while the next queries are being searched (the one place where a
+// kernel is directly followed by a collective).
+constexpr int KNN_MAX_PEERS = 16;
+struct KnnPeers {
+    int npeers;
+    int64_t row_base;
+    int* idx[KNN_MAX_PEERS];
+    float* dist[KNN_MAX_PEERS];
+};
+
 template <int KPL>
 __global__ void __launch_bounds__(256) knn_grid_kernel(int64_t m, int k, int b, const float* __restrict__ xyz,
                                                        const float* __restrict__ new_xyz,
@@ -344,7 +357,7 @@ __global__ void __launch_bounds__(256) knn_grid_kernel(int64_t m, int k, int b, 
                                                        const float4* __restrict__ sorted, int* __restrict__ idx_out,
                                                        float* __restrict__ dist_out, float* __restrict__ weight_out,
                                                        int take_sqrt, int force_brute,
-                                                       unsigned long long* __restrict__ stats) {
+                                                       unsigned long long* __restrict__ stats, const KnnPeers peers) {
     const int lane = threadIdx.x & 31;
     const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= m) return;
@@ -439,9 +452,19 @@ __global__ void __launch_bounds__(256) knn_grid_kernel(int64_t m, int k, int b, 
         recip[r] = 0.f;
         if (e < k) {
             const bool real = t.i[r] != INT_MAX;
-            idx_out[q * k + e] = real ? t.i[r] : -1;
             const float d2 = real ? t.d[r] : PLACEHOLDER_D2;
-            if (dist_out) dist_out[q * k + e] = take_sqrt ? __fsqrt_rn(d2) : d2;
+            if (peers.npeers == 0) {
+                idx_out[q * k + e] = real ? t.i[r] : -1;
+                if (dist_out) dist_out[q * k + e] = take_sqrt ? __fsqrt_rn(d2) : d2;
+            } else {
+                const int64_t at = (peers.row_base + q) * k + e;
+                const int vi = real ? t.i[r] : -1;
+                const float vd = take_sqrt ? __fsqrt_rn(d2) : d2;
+                for (int g = 0; g < peers.npeers; g++) {
+                    peers.idx[g][at] = vi;
+                    if (peers.dist[g]) peers.dist[g][at] = vd;
+                }
+            }
             // functions/interpolation.py:15: 1 / (sqrt(d2) + 1e-8)
             recip[r] = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(d2), 1e-8f));
             rsum += recip[r];
@@ -730,11 +753,13 @@ POB_API int pob_knn_grid_build(int64_t n, int b, const float* xyz, const int* of
 static int knn_launch(int64_t m, int k, int b, const float* xyz, const float* new_xyz, const int* new_offset,
                       const SceneGrid* scenes, const int* cell_start, const float4* sorted, int* idx, float* dist,
                       float* weight, int take_sqrt, int force_brute, cudaStream_t stream,
-                      unsigned long long* stats = nullptr) {
+                      unsigned long long* stats = nullptr, const KnnPeers* peers_in = nullptr) {
+    KnnPeers peers = {};
+    if (peers_in) peers = *peers_in;
     const unsigned blocks = (unsigned)ceil_div(m, 8);
 #define POB_KNN_LAUNCH(KPL)                                                                                       \
     knn_grid_kernel<KPL><<<blocks, 256, 0, stream>>>(m, k, b, xyz, new_xyz, new_offset, scenes, cell_start, sorted, \
-                                                     idx, dist, weight, take_sqrt, force_brute, stats)
+                                                     idx, dist, weight, take_sqrt, force_brute, stats, peers)
     if (k <= 32) POB_KNN_LAUNCH(1);
     else if (k <= 64) POB_KNN_LAUNCH(2);
     else if (k <= 128) POB_KNN_LAUNCH(4);
@@ -756,6 +781,35 @@ POB_API int pob_knn_grid_query(int64_t m, int nsample, int64_t n, int b, const f
     return knn_launch(m, nsample, b, xyz, new_xyz, new_offset, (const SceneGrid*)(ws + L.off_scene),
                       (const int*)(ws + L.off_start), (const float4*)(ws + L.off_sorted), idx, dist, weight, take_sqrt,
                       0, stream, (unsigned long long*)stats_u64);
+}
+
+// Query a built grid and store every result row into the (n_total, nsample) result buffers of ALL ranks: peer_idx /
+// peer_dist are HOST arrays of npeers device pointers (peer-mapped: cudaMalloc + IPC / symmetric memory; the caller's
+// own buffer is one of them), row_base is where this rank's first query row goes.  peer_dist may be NULL, or hold
+// NULLs.  Synchronisation with the peers (nobody reads before everybody has written) is the caller's.
+POB_API int pob_knn_grid_query_scatter(int64_t m, int nsample, int64_t n, int b, const float* xyz, const float* new_xyz,
+                                       const int* new_offset, float cell_pts, const void* workspace, int64_t row_base,
+                                       int npeers, int* const* peer_idx, float* const* peer_dist, int take_sqrt,
+                                       cudaStream_t stream) {
+    if (m < 0 || nsample < 1 || nsample > 256 || b < 1 || !workspace || npeers < 1 || npeers > KNN_MAX_PEERS || !peer_idx ||
+        row_base < 0)
+        return POB_ERR_BAD_ARG;
+    if (m == 0) return 0;
+    if (!new_xyz || !new_offset) return POB_ERR_BAD_ARG;
+    if (!(cell_pts >= 0.25f)) cell_pts = 0.25f;
+    const GridLayout L = grid_layout(n, b, cell_pts);
+    const char* ws = (const char*)workspace;
+    KnnPeers peers = {};
+    peers.npeers = npeers;
+    peers.row_base = row_base;
+    for (int g = 0; g < npeers; g++) {
+        if (!peer_idx[g]) return POB_ERR_BAD_ARG;
+        peers.idx[g] = peer_idx[g];
+        peers.dist[g] = peer_dist ? peer_dist[g] : nullptr;
+    }
+    return knn_launch(m, nsample, b, xyz, new_xyz, new_offset, (const SceneGrid*)(ws + L.off_scene),
+                      (const int*)(ws + L.off_start), (const float4*)(ws + L.off_sorted), nullptr, nullptr, nullptr, take_sqrt,
+                      0, stream, nullptr, &peers);
 }
 
 // Reference-shaped entry point: knn_query_cuda_launcher (knn_query_cuda_kernel.h:13) plus the

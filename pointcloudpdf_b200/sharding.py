@@ -98,6 +98,62 @@ def sharded_knn_query(nsample: int, xyz: torch.Tensor, offset: torch.Tensor, off
     return idx, dst
 
 
+# ------------------------------------------------------------ fused query + all-gather --
+# The all-gather above moves every result row twice (kernel -> local shard -> NCCL -> assembled result) and costs
+# more than the search itself once the queries are split 8 ways (2 M x 32 results = 512 MB of idx + dist).  The
+# fused form gives the query kernel the peer-mapped result buffers of ALL ranks (torch symmetric memory:
+# cudaMalloc'ed, exchanged once through CUDA IPC / fabric handles) and lets it store each result row straight into
+# every rank's (n, k) result over NVLink / NVSwitch -- the transfer overlaps the search warp by warp, and no
+# assembly copy is left.  One device-side barrier over the symmetric signal pads closes the step.
+
+_SYMM = {}
+
+
+def _symm_buffers(n: int, k: int, device, group):
+    """(idx, dist, handle_idx, handle_dist) symmetric (n, k) result buffers, rendezvoused once per shape."""
+    import torch.distributed._symmetric_memory as symm_mem
+    gname = group.group_name if group is not None else dist.group.WORLD.group_name
+    key = (n, k, device.index, gname)
+    hit = _SYMM.get(key)
+    if hit is None:
+        idx = symm_mem.empty((n, k), dtype=torch.int32, device=device)
+        dst = symm_mem.empty((n, k), dtype=torch.float32, device=device)
+        hit = _SYMM[key] = (idx, dst, symm_mem.rendezvous(idx, gname), symm_mem.rendezvous(dst, gname))
+    return hit
+
+
+def sharded_knn_query_fused(nsample: int, xyz: torch.Tensor, offset: torch.Tensor, offset_host: Sequence[int], group=None):
+    """Same contract as sharded_knn_query (full (n, nsample) idx and dist on every rank, bit-identical to the
+    single-GPU result) with the all-gather fused into the query kernel: P2P stores into every rank's result
+    buffer (pob_knn_grid_query_scatter).  Single-scene clouds (the cfg5 case); the returned tensors are the
+    symmetric buffers themselves and are overwritten by the next call of the same shape."""
+    import ctypes
+    from . import _lib
+    from .pointops import _common as C
+    if len(offset_host) != 1:
+        raise ValueError("the fused form shards one large scene; batches shard by scene (shard_scenes)")
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n, dev = int(xyz.shape[0]), xyz.device
+    if world == 1:
+        return C.get_grid(xyz, offset).query(nsample, xyz, offset, True, False)[:2]
+    idx, dst, h_idx, h_dst = _symm_buffers(n, int(nsample), dev, group)
+    (lo, hi), = query_slices(offset_host, rank, world)[0]
+    grid = C.get_grid(xyz, offset)
+    q = xyz[lo:hi]                                  # a contiguous slice: no copy
+    new_offset = C.const_offset([hi - lo], dev)
+    PtrArr = ctypes.c_void_p * world
+    pi = PtrArr(*[int(p) for p in h_idx.buffer_ptrs])
+    pd = PtrArr(*[int(p) for p in h_dst.buffer_ptrs])
+    h_idx.barrier(channel=0)                        # nobody is still reading the previous result
+    _lib.run("pob_knn_grid_query_scatter", hi - lo, int(nsample), grid.n, grid.b, _lib.ptr(xyz), _lib.ptr(q),
+             _lib.ptr(new_offset), grid.cell_pts, _lib.ptr(grid.workspace), lo, world,
+             ctypes.cast(pi, ctypes.c_void_p), ctypes.cast(pd, ctypes.c_void_p), 1, _lib.current_stream(dev),
+             alg_bytes=12 * n + 12 * (hi - lo) + 8 * nsample * (hi - lo) * world)
+    h_idx.barrier(channel=1)                        # every rank's rows have landed everywhere
+    return idx, dst
+
+
 def allreduce_gradients(params, group=None, bucket_bytes: int = 32 << 20) -> None:
     """Average gradients over the ranks in a few flat buckets (what DDP's hooks do)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

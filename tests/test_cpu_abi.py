@@ -56,7 +56,7 @@ def test_no_compute_needed_entry_points(lib):
     assert b"workspace" in lib.pob_error_string(10002)
     assert lib.pob_knn_grid_workspace_bytes(80000, 1, 2.0) > 80000 * 20
     assert lib.pob_knn_grid_workspace_bytes(-1, 1, 2.0) == 0
-    assert lib.pob_score_workspace_bytes(4) == 256
+    assert lib.pob_score_workspace_bytes(4) == 64 * (4 + 1)   # b scene slots + the finished-blocks counter
 
 
 def test_python_surface_matches_reference_names():

@@ -123,3 +123,49 @@ def test_reference_functions_package_over_reference_kernels_equals_product_ops(c
     assert torch.equal(m_idx, r_idx) and torch.equal(m_g, r_g)
     m_up = mine.interpolation(n_p, xyz, feat[m_fps.long()].contiguous(), noff, off)
     assert float((m_up - r_up).abs().max() / r_up.abs().max()) <= 1e-5
+
+
+def test_reference_functions_over_the_compiled_C_shim(cuda, gold, glue):
+    """the reference's own python wrappers (libs/pointops/functions/*.py, unmodified) over
+    integration/pointops_C_shim.cpp -- a compiled `pointops._C` with the reference's signatures on top of the C ABI.
+    Operators against this repo's package, then the whole unmodified model against the golden logits."""
+    import pointops as mine
+    from pointcloudpdf_b200 import synthetic as S
+    b = S.s3dis_batch([6000, 2500], seed=78)
+    xyz, feat, off = b["coord"].to(cuda), b["feat"].to(cuda), b["offset"].to(cuda)
+    noff = torch.tensor([1500, 2125], dtype=torch.int32, device=cuda)
+    g = torch.Generator(device=cuda).manual_seed(3)
+    with glue.reference_modules("shim") as R:
+        po = R.pointops
+        assert type(sys_modules_C()).__name__ == "module"
+        r_fps = po.farthest_point_sampling(xyz, off, noff)
+        n_p = xyz[r_fps.long()].contiguous()
+        r_g, r_idx = po.knn_query_and_group(feat, xyz, offset=off, new_xyz=n_p, new_offset=noff, nsample=16, with_xyz=True)
+        r_up = po.interpolation(n_p, xyz, feat[r_fps.long()].contiguous(), noff, off)
+        idx16, _ = po.knn_query(16, xyz, off)
+        x = torch.randn(xyz.shape[0], 32, device=cuda, generator=g).requires_grad_(True)
+        pos = torch.randn(xyz.shape[0], 16, 32, device=cuda, generator=g)
+        w = torch.softmax(torch.randn(xyz.shape[0], 16, 4, device=cuda, generator=g), 1)
+        r_agg = po.aggregation(x, pos, w, idx16)
+        r_agg.sum().backward()
+        r_gx = x.grad.clone()
+        torch.cuda.synchronize()
+    assert torch.equal(mine.farthest_point_sampling(xyz, off, noff), r_fps)
+    m_g, m_idx = mine.knn_query_and_group(feat, xyz, offset=off, new_xyz=n_p, new_offset=noff, nsample=16, with_xyz=True)
+    assert torch.equal(m_idx, r_idx) and torch.equal(m_g, r_g)
+    m_up = mine.interpolation(n_p, xyz, feat[r_fps.long()].contiguous(), noff, off)
+    assert float((m_up - r_up).abs().max() / r_up.abs().max()) <= 1e-5
+    x2 = x.detach().clone().requires_grad_(True)
+    m_agg = mine.aggregation(x2, pos, w, mine.knn_query(16, xyz, off)[0])
+    assert float((m_agg - r_agg).abs().max() / r_agg.abs().max()) <= 1e-5
+    m_agg.sum().backward()
+    assert float((x2.grad - r_gx).abs().max() / r_gx.abs().max()) <= 1e-5
+    logits, msp, conf = run_reference_callers(glue, "shim", gold, cuda)
+    assert (logits - gold["logits"]).abs().max() <= 2e-4
+    assert (msp - gold["msp"]).abs().max() <= 1e-4
+    assert (conf - gold["conf"]).abs().max() <= 2e-4
+
+
+def sys_modules_C():
+    import sys
+    return sys.modules["pointops._C"]
