@@ -649,11 +649,15 @@ static int launch_group_xyz_fwd_fast(int lpr, int64_t m, int ns, const T* feat, 
     const int per = ns * (4 * lpr + 3);
     const size_t smem = sizeof(float) * (size_t)((per + 3) & ~3) * (FAST_THREADS / 32);
     if (smem > 200 * 1024 || ns > 32) return -1;   // the kernel keeps one neighbour index per lane
-#define M(L) { auto kern = group_xyz_fwd_fast<T, L>; \
+    // passes per chunk: all of them for the PTv1 neighbourhood sizes (ns = 8 / 16), at most 8 gathers in flight per lane
+#define K(L, CHV) { auto kern = group_xyz_fwd_fast<T, L, CHV>; \
         if (smem > 48 * 1024) POB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<fast_grid(m), FAST_THREADS, smem, stream>>>(m, ns, feat, xyz, new_xyz, idx, out); }
+#define M(L) { constexpr int SP_ = 32 / L; const int need = (ns + SP_ - 1) / SP_; \
+        if (need <= 1) K(L, 1) else if (need <= 2) K(L, 2) else if (need <= 4) K(L, 4) else K(L, 8) }
     POB_LPR_SWITCH(lpr, M)
 #undef M
+#undef K
     return 0;
 }
 

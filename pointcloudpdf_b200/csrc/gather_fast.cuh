@@ -177,7 +177,7 @@ interpolation_fwd_fast(int64_t n, int k, const float4* __restrict__ in, const in
 // ns rows of one query are one contiguous span of ns*W floats: each warp assembles that span in
 // shared memory (128-bit gathers in, conflict-free scalar stores) and streams it out with
 // 128-bit stores.  Dynamic shared memory: warps_per_cta * ns * W floats.
-template <typename T, int LPR>
+template <typename T, int LPR, int CH>
 __global__ void __launch_bounds__(FAST_THREADS)
 group_xyz_fwd_fast(int64_t m, int ns, const T* __restrict__ feat, const float* __restrict__ xyz,
                    const float* __restrict__ new_xyz, const int* __restrict__ idx, float* __restrict__ out) {
@@ -199,8 +199,8 @@ group_xyz_fwd_fast(int64_t m, int ns, const T* __restrict__ feat, const float* _
             dy = __fsub_rn(__ldg(xyz + (int64_t)my_src * 3 + 1), qy);
             dz = __fsub_rn(__ldg(xyz + (int64_t)my_src * 3 + 2), qz);
         }
-        // the gathers of up to CH passes are issued before anything is stored (independent 16-byte loads per lane)
-        constexpr int CH = (32 / SPAR) < 8 ? (32 / SPAR) : 8;      // ns <= 32 here (the launcher checks)
+        // the gathers of CH passes (CH * SPAR rows; the launcher picks CH so that ns = 8 / 16 take one chunk) are
+        // issued before anything is stored: independent 16-byte loads per lane.  ns <= 32 (one index per lane).
         for (int s0 = 0; s0 < ns; s0 += CH * SPAR) {
             float4 v[CH];
 #pragma unroll

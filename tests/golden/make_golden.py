@@ -89,9 +89,37 @@ def ptv1_small(R):
     return model, rec_model
 
 
+def pseudo_small():
+    """Region growth of PointPdfV1.pseudo_labeling, produced by the REFERENCE's own function (oracle/pseudo_oracle.py
+    ::reference_growth runs the unmodified staticmethod and captures the region at the end of its growth loop).  Scenes
+    carry a planted low-confidence blob so that the region really grows (hundreds of points, dozens of iterations)."""
+    from oracle import pseudo_oracle as PO
+    cases = []
+    for n, seed, radius, sw in ((3000, 31, 0.06, False), (3000, 31, 0.06, True), (4000, 32, 0.05, False), (2500, 33, 0.07, True)):
+        b = S.scannet_batch([n], seed=seed)
+        coord = b["coord"]
+        g = torch.Generator().manual_seed(seed)
+        label = torch.randint(0, 20, (n,), generator=g)
+        logits = torch.randn(n, 20, generator=g) * 0.7
+        logits[torch.arange(n), label] += 5.0
+        centre = coord[torch.randint(0, n, (1,), generator=g)]
+        blob = (coord - centre).norm(dim=-1) < 0.3 * float((coord.max(0)[0] - coord.min(0)[0]).max())
+        logits[blob] = torch.randn(int(blob.sum()), 20, generator=g) * 0.3     # flat logits: low msp, low max logit
+        batch = torch.zeros(n, dtype=torch.long)
+        nbrs, _ = PO.ball_query_partial_dense(radius, 16, coord, coord, batch, batch)
+        region = PO.reference_growth(coord, logits, nbrs, "msp", 1.0, "ml", 0.15, 30, sw, seed=1000 + seed)
+        # neighbours are not stored (the oracle recomputes them from coord / radius in a second)
+        cases.append(dict(coord=coord, logits=logits.half().float() if False else logits, radius=radius, max_neighbor=16, condition_from="msp",
+                          beta=1.0, seed_from="ml", seed_range=0.15, num_seed=30, slide_window=sw, torch_seed=1000 + seed,
+                          region=region, blob=int(blob.sum())))
+        print("pseudo_small", n, sw, "blob", int(blob.sum()), "region", region.numel())
+    torch.save(cases, os.path.join(HERE, "pseudo_small.pt"))
+
+
 if __name__ == "__main__":
     with ref_glue.reference_modules() as R:
         ops_small(R)
         scores_small(R)
         ptv1_small(R)
+    pseudo_small()
     print("golden fixtures written to", HERE)

@@ -17,6 +17,7 @@ f, f2 = mk(N, Cc), mk(N, Cc)
 for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
     flush.zero_(); pointops.grouping(idx, f, xyz, xyz, True)
     flush.zero_(); pointops.grouping2(f, idx)
-    flush.zero_(); pointops.subtraction(f, f2, idx)
+    flush.zero_(); o = pointops.subtraction(f.requires_grad_(True), f2.requires_grad_(True), idx)
+    flush.zero_(); o.backward(mk(N, ns, Cc))
 torch.cuda.synchronize()
 print("done")

@@ -1,0 +1,114 @@
+"""Side measurements for the BASELINE configs that are parity cases rather than the bench line, on one GPU:
+cfg4 (PDF U-decoder inference on 150 000-point ScanNet-shaped scenes + the fused scoring pass as GB/s vs the HBM
+peak) and cfg5 (large single-scene FPS + kNN sweep 100 k - 2 M points).  cfg3 and the sharded cfg5 kNN are part of
+bench.py --gpus N.      python tools/side_benches.py [out.json]"""
+import json, os, sys, time, statistics
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from pointcloudpdf_b200 import synthetic as S
+from pointcloudpdf_b200.ptv1 import OpenSegPTv1
+from pointcloudpdf_b200.scoring import fused_scores
+from pointcloudpdf_b200.pointops import _common as C
+import pointcloudpdf_b200.pointops as pointops
+
+dev = torch.device("cuda:0")
+torch.backends.cuda.matmul.allow_tf32 = False
+try:
+    HBM = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    HBM = 6650.0
+out = {"hbm_peak_GBps": HBM}
+
+
+def graph_time(fn, reps=24):
+    """mean us per launch: `reps` launches in one CUDA graph, events around a replay, median of 5"""
+    fn(); torch.cuda.synchronize()
+    st = torch.cuda.Stream(device=dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=st, capture_error_mode="thread_local"):
+        for _ in range(reps):
+            fn()
+    ts = []
+    with torch.cuda.stream(st):
+        g.replay()
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st); g.replay(); e1.record(st); e1.synchronize(); ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts) / reps * 1e3
+
+
+def ev_time(fn, warm=1, reps=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize(); ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
+with torch.no_grad():
+    # ---- scoring pass (a9 / a10 / a11) as bandwidth: rotating inputs larger than L2 in total are not needed for a
+    #      streaming kernel whose inputs (5-14 MB) are evicted by the 24 distinct output sets it writes ----
+    rows = []
+    for n, K, what, want, use_conf, use_off in (
+            (80000, 13, "msp score + pred (the bench's recognizer pass)", ("msp_score", "pred"), False, False),
+            (150000, 20, "pdf score (+conf) + pred (cfg4 eval)", ("pdf_score", "pred"), True, False),
+            (150000, 20, "pseudo-label prefix: msp_prob, ml_norm + per-scene stats (cfg4 training)", ("msp_prob", "ml_norm"), False, True)):
+        lg, conf, _u, _l = S.openset_logits(n, K)
+        lgs = [lg.to(dev).clone() for _ in range(8)]
+        cf = conf.to(dev).reshape(-1).contiguous()
+        off = torch.tensor([n // 2, n], dtype=torch.int32, device=dev)
+        i = [0]
+
+        def run():
+            i[0] += 1
+            fused_scores(lgs[i[0] % 8], cf if use_conf else None, offset=off if use_off else None, beta=1.5, want=want)
+        us = graph_time(run)
+        n_out = len(want) + (1 if "ml_norm" in want else 0)
+        nbytes = 4 * n * (K + (1 if use_conf else 0) + n_out)
+        rows.append({"n": n, "K": K, "what": what, "us": us, "alg_MB": nbytes / 1e6, "GBps": nbytes / us / 1e3, "frac_of_hbm_peak": nbytes / us / 1e3 / HBM})
+        print(rows[-1], flush=True)
+    out["scoring_pass"] = rows
+
+    # ---- cfg4: PDF U-decoder + fused score on 150 000-point ScanNet-shaped scenes ----
+    torch.manual_seed(2024)
+    net = OpenSegPTv1(in_channels=9, num_classes=20, method="pdf").to(dev).eval()
+    rooms = [S.scannet_batch([150000], seed=3000 + i) for i in range(3)]
+    seq = [(r["coord"].pin_memory(), r["feat"].pin_memory(), r["offset"]) for r in rooms]
+    run = lambda k: [None for _ in net.infer_stream([seq[i % 3] for i in range(k)], depth=6)]
+    run(8); torch.cuda.synchronize()
+    secs = []
+    for _ in range(3):
+        t0 = time.perf_counter(); run(36); torch.cuda.synchronize(); secs.append(time.perf_counter() - t0)
+    sec = statistics.median(secs)
+    out["cfg4_pdf_inference"] = {"points_per_room": 150000, "classes": 20, "rooms": 36, "ms_per_room": sec / 36 * 1e3, "points_per_sec": 36 * 150000 / sec,
+                                 "what": "backbone + PDF U-decoder + fused softmax score, host buffers in / out, graph replay, 6 rooms in flight; "
+                                         "the 150 000-point FPS stage runs the grid-wide kernel"}
+    print(out["cfg4_pdf_inference"], flush=True)
+    del net; torch.cuda.empty_cache(); C.clear_caches()
+
+    # ---- cfg5: large single scene, one GPU ----
+    out["cfg5_knn"], out["cfg5_fps"] = [], []
+    for n in (100000, 250000, 500000, 1000000, 2000000):
+        b = S.s3dis_batch([n], seed=2029)
+        xyz, off = b["coord"].to(dev), b["offset"].to(dev)
+        for k in (16, 32):
+            def run_knn():
+                C.clear_caches()
+                return C.get_grid(xyz, off).query(k, xyz, off, True, False)
+            ms = ev_time(run_knn, warm=1, reps=3)
+            out["cfg5_knn"].append({"n": n, "k": k, "ms": ms, "queries_per_sec": n / ms * 1e3})
+        m = n // 4
+        noff = torch.tensor([m], dtype=torch.int32, device=dev)
+
+        def run_fps():
+            C.clear_caches()
+            return pointops.farthest_point_sampling(xyz, off, noff)
+        ms = ev_time(run_fps, warm=1, reps=2)
+        out["cfg5_fps"].append({"n": n, "m": m, "ms": ms, "ns_per_sample": ms * 1e6 / m, "includes": "grid build",
+                                "kernel": "cluster (registers / shared memory)" if n <= 131072 else ("grid-wide cooperative" if n <= 148 * 8192 else "streamed")})
+        print(out["cfg5_fps"][-1], flush=True)
+        del xyz, off; torch.cuda.empty_cache()
+path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/side_benches.json"
+json.dump(out, open(path, "w"), indent=1)
