@@ -10,8 +10,11 @@
  *   - a trailing cudaStream_t (the reference launches on the legacy default stream),
  *   - an int return: 0 on success, a cudaError_t from the launch, or a POB_ERR_* code;
  *   - where a kernel needs scratch, a caller-owned workspace with a *_workspace_bytes query.
- * No entry point allocates, frees, synchronises or reads device data on the host, so all of
- * them are re-entrant, stream-ordered and CUDA-graph capturable.  All pointers are device
+ * No entry point allocates, frees, synchronises or reads device data on the host, and the library keeps
+ * NO tuning state between calls (every schedule / tile / variant choice is an argument of the call): all of
+ * them are re-entrant, stream-ordered and CUDA-graph capturable.  The only process-wide data are an atomic
+ * launch counter (pob_kernel_launch_count) and one environment switch read once at load time
+ * (POINTOPS_B200_NO_PIPE: aggregation forward without the bulk-async ring).  All pointers are device
  * pointers unless stated otherwise.  Tensors are dense row-major, f32 / i32 as in the reference.
  *
  * Batched-by-offset convention (libs/pointops/functions/query.py:9-24): a batch is the
@@ -221,10 +224,9 @@ int64_t pob_pt_layer_param_floats(int c, int w_c);
  * 1, 4, 8, 16: the warp-per-point kernel with that many warps sharing one point (clamped to what the
  * shape instantiates); -1: warp-per-point with the split chosen from n.  Only the f32 summation order
  * depends on it.                                                                                   */
-int pob_pt_layer_set_split(int warps_per_point);
 int pob_pt_layer_forward(int64_t n, int nsample, int c, int w_c, const float* q, int64_t ldq, const float* k,
                          int64_t ldk, const float* v, int64_t ldv, const float* xyz, const int* idx,
-                         const float* params, int out_affine, float* out, int64_t ldo, cudaStream_t stream);
+                         const float* params, int out_affine, float* out, int64_t ldo, int split, cudaStream_t stream);
 /* out = relu?(x * scale + shift + residual) over (rows, c); scale, shift (c) and residual (rows, c) may be
  * NULL; in place allowed.  The BN / skip / ReLU tail of Bottleneck (point_transformer_seg.py:188-195).  */
 int pob_affine_act(int64_t rows, int c, const float* x, const float* scale, const float* shift,
@@ -250,12 +252,12 @@ int pob_interpolation_add_forward(int64_t n, int c, int k, const float* input, c
  * Wt is the weight stored dense K x N (the caller transposes the constant once).  FP32 FFMA, operands are
  * not rounded to TF32.  Any K, N >= 1 (scalar loads / stores when K, N, strides or pointers are not
  * 16-byte friendly).  out must not alias A or residual (both are read through the read-only path).
- * pob_linear_set_config: test / tuning hook, 0 (default) picks the CTA tile from the shape, 1..16 force one of
+ * config (per call; the library keeps no tuning state): test / tuning hook, 0 (default) picks the CTA tile from the shape, 1..16 force one of
  * the instantiated tiles (BM x BN from 16x32 to 256x32 / 128x64, register tiles 4x4, 8x4 or 8x8, intra-CTA
  * split-K 1..8; csrc/linear.cu lists them).  Only the f32 summation order depends on it.                   */
-int pob_linear_set_config(int config);
 int pob_linear_forward(int64_t M, int K, int N, const float* A, int64_t lda, const float* Wt, const float* bias,
-                       const float* residual, int64_t ldr, int relu, float* out, int64_t ldo, cudaStream_t stream);
+                       const float* residual, int64_t ldr, int relu, float* out, int64_t ldo, int config,
+                       cudaStream_t stream);
 
 /* ------------------------------------------------------- grouped vector attention steps --
  * (off the PTv1 path: Point Transformer v2's operators)  Replace the four launchers of

@@ -45,13 +45,11 @@ SIGNATURES = {
     "pob_group_xyz_backward": (I, [L, I, I, I, P, P, P, P]),
     "pob_group_relxyz_forward": (I, [L, I, P, P, P, P, P]),
     "pob_pt_layer_param_floats": (L, [I, I]),
-    "pob_pt_layer_set_split": (I, [I]),
-    "pob_pt_layer_forward": (I, [L, I, I, I, P, L, P, L, P, L, P, P, P, I, P, L, P]),
+    "pob_pt_layer_forward": (I, [L, I, I, I, P, L, P, L, P, L, P, P, P, I, P, L, I, P]),
     "pob_affine_act": (I, [L, I, P, P, P, P, I, P, P]),
     "pob_transition_down_pool": (I, [L, I, I, P, P, P, P, P, P, P, P, P]),
     "pob_interpolation_add_forward": (I, [L, I, I, P, P, P, P, P, P]),
-    "pob_linear_set_config": (I, [I]),
-    "pob_linear_forward": (I, [L, I, I, P, L, P, P, P, L, I, P, L, P]),
+    "pob_linear_forward": (I, [L, I, I, P, L, P, P, P, L, I, P, L, I, P]),
     "pob_attention_relation_step_forward": (I, [L, I, I, P, P, P, P, P, P, P]),
     "pob_attention_relation_step_backward": (I, [L, I, I, P, P, P, P, P, P, P, P, P, P]),
     "pob_attention_fusion_step_forward": (I, [L, I, I, P, P, P, P, P, P]),

@@ -3,7 +3,7 @@
 // FPS is "argmax, update, argmax, ..." -- one cluster-wide exchange per sample in the plain form.  The round-1
 // chain kernel accepted ~4.5 samples per exchange (every CTA offers ONE candidate plus a bound on what would
 // follow it).  This kernel generalises that to whole LISTS and reaches ~20 samples per exchange on S3DIS-shaped
-// rooms (scratch/fps_merge_sim.py: 80 000 -> 20 000 points in 1 010 rounds instead of 4 444, output identical
+// rooms (tools/fps_merge_sim.py: 80 000 -> 20 000 points in 1 010 rounds instead of 4 444, output identical
 // to one-at-a-time FPS in every configuration simulated):
 //
 //   * every warp owns a spatially compact run of 32*P points (cell order of the kNN grid) and keeps, next to

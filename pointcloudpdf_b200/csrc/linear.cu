@@ -248,17 +248,9 @@ static int launch_linear_unaligned(int64_t M, int K, int N, bool vec_k, bool vec
 
 using namespace pob;
 
-static int g_linear_force = 0;   // 0 = pick the tile from the shape; 1..POB_LINEAR_CONFIGS = force one (tests, tuning)
+#define POB_LINEAR_CONFIGS 16   // `config` (per call): 0 = pick the tile from the shape; 1..16 = force one (tests, tuning)
 
-#define POB_LINEAR_CONFIGS 16
-
-POB_API int pob_linear_set_config(int config) {
-    if (config < 0 || config > POB_LINEAR_CONFIGS) return POB_ERR_BAD_ARG;
-    g_linear_force = config;
-    return 0;
-}
-
-// Tile choice, from the per-shape timings of scratch/linear_time.py on B200 (profiles/): the shapes are skinny
+// Tile choice, from the per-shape timings on B200 (profiles/r01d_linear_time.txt): the shapes are skinny
 // and small (0.16-0.5 GFLOP), so a launch is latency bound -- what matters is >= ~2 CTAs per SM with as many
 // warps as possible in flight, split-K where the rows alone do not provide them.  8 x 8 register tiles only
 // pay for the widest outputs.
@@ -276,9 +268,11 @@ static int pick_linear_config(int64_t M, int K, int N) {
 // 128-bit paths when K, N, the strides and the pointers are 16-byte friendly, scalar loads / stores otherwise.
 // out must not alias A or residual (both are read through the read-only data path).
 POB_API int pob_linear_forward(int64_t M, int K, int N, const float* A, int64_t lda, const float* Wt, const float* bias,
-                               const float* residual, int64_t ldr, int relu, float* out, int64_t ldo,
+                               const float* residual, int64_t ldr, int relu, float* out, int64_t ldo, int config,
                                cudaStream_t stream) {
-    if (M < 0 || K < 1 || N < 1 || lda < K || ldo < N || (residual && ldr < N)) return POB_ERR_BAD_ARG;
+    if (M < 0 || K < 1 || N < 1 || lda < K || ldo < N || (residual && ldr < N) || config < 0 || config > POB_LINEAR_CONFIGS)
+        return POB_ERR_BAD_ARG;
+    const int g_linear_force = config;
     if (M == 0) return 0;
     if (!A || !Wt || !out) return POB_ERR_BAD_ARG;
     const bool vec_k = K % 4 == 0 && lda % 4 == 0 && al16p(A);

@@ -683,11 +683,9 @@ static inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 using namespace pob;
 
-// tuning / test hook: 0 (default) = the CTA-tiled kernel (16-byte aligned rows; otherwise warp-per-point);
-// 1, 4, 8, 16 = force the warp-per-point kernel with that many warps sharing a point (clamped to what the
-// shape instantiates); -1 = warp-per-point with the split chosen from n.  Only f32 summation order differs.
-static int g_ptl_split = 0;
-POB_API int pob_pt_layer_set_split(int warps_per_point) { g_ptl_split = warps_per_point; return 0; }
+// `split` (per call; tests / tuning): 0 (default) = the CTA-tiled kernel (16-byte aligned rows; otherwise
+// warp-per-point); 1, 4, 8, 16 = force the warp-per-point kernel with that many warps sharing a point (clamped to
+// what the shape instantiates); -1 = warp-per-point with the split chosen from n.  Only f32 summation order differs.
 
 POB_API int64_t pob_pt_layer_param_floats(int c, int w_c) {
     if (c < 1 || w_c < 1) return 0;
@@ -702,7 +700,9 @@ POB_API int64_t pob_pt_layer_param_floats(int c, int w_c) {
 // Supported: c in {32, 64, 128, 256, 512} with w_c = c / 8 (share_planes = 8), nsample in {8, 16}.
 POB_API int pob_pt_layer_forward(int64_t n, int nsample, int c, int w_c, const float* q, int64_t ldq, const float* k,
                                  int64_t ldk, const float* v, int64_t ldv, const float* xyz, const int* idx,
-                                 const float* params, int out_affine, float* out, int64_t ldo, cudaStream_t stream) {
+                                 const float* params, int out_affine, float* out, int64_t ldo, int split,
+                                 cudaStream_t stream) {
+    const int g_ptl_split = split;
     if (n < 0 || nsample < 1 || c < 1 || w_c < 1) return POB_ERR_BAD_ARG;
     if (n == 0) return 0;
     if (!q || !k || !v || !xyz || !idx || !params || !out) return POB_ERR_BAD_ARG;

@@ -43,9 +43,10 @@ def pack_pt_layer_params(A, cvec, wp, bp, aw, bw, w1, b1, w2, b2, oa, ob) -> tor
 
 
 def pt_layer_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, xyz: torch.Tensor, idx: torch.Tensor,
-                     params: torch.Tensor, out_affine: bool = True) -> torch.Tensor:
+                     params: torch.Tensor, out_affine: bool = True, split: int = 0) -> torch.Tensor:
     """Eval-mode PointTransformerLayer (+ optional BN/ReLU tail) on q, k, v (n, C) -- which may be
-    column slices of one (n, 3C) tensor -- coordinates xyz (n, 3) and the self-kNN idx (n, ns) i32."""
+    column slices of one (n, 3C) tensor -- coordinates xyz (n, 3) and the self-kNN idx (n, ns) i32.
+    split (per call, tests / tuning): 0 = the CTA-tiled kernel, 1 / 4 / 8 / 16 / -1 = the warp-per-point forms."""
     n, c = q.shape
     ns = idx.shape[1]
     for name, t in (("q", q), ("k", k), ("v", v)):
@@ -63,7 +64,7 @@ def pt_layer_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, xyz: tor
     with _lib.device_guard(q.device):
         _lib.run("pob_pt_layer_forward", n, ns, c, wc, _lib.ptr(q), q.stride(0), _lib.ptr(k), k.stride(0),
                  _lib.ptr(v), v.stride(0), _lib.ptr(xyz), _lib.ptr(idx), _lib.ptr(params), int(bool(out_affine)),
-                 _lib.ptr(out), c, _lib.current_stream(q.device),
+                 _lib.ptr(out), c, int(split), _lib.current_stream(q.device),
                  # compulsory traffic: q, k, v tables, coordinates, indices, output, once each
                  alg_bytes=4 * (4 * n * c + 3 * n + n * ns) + 4 * params.numel(),
                  alg_flops=2 * n * ns * (9 + 3 * c + c * wc + wc * wc + 2 * c),
@@ -75,10 +76,11 @@ def pt_layer_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, xyz: tor
 
 
 def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = None,
-           residual: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+           residual: Optional[torch.Tensor] = None, relu: bool = False, config: int = 0) -> torch.Tensor:
     """act(x @ wt + bias + residual): FP32 linear with the epilogue applied on the accumulators
     (``pob_linear_forward``).  x (M, K) f32 with unit column stride (a column block of a wider tensor is
-    fine), wt (K, N) dense -- the Linear weight transposed once --, bias (N), residual (M, N)."""
+    fine), wt (K, N) dense -- the Linear weight transposed once --, bias (N), residual (M, N).
+    config (per call, tests / tuning): 0 = tile picked from the shape, 1..16 = force one instantiation."""
     if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
         raise ValueError("linear: x must be a CUDA f32 (M, K) tensor with unit column stride")
     C.require(wt, "wt", torch.float32, 2)
@@ -100,7 +102,7 @@ def linear(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = Non
     with _lib.device_guard(x.device):
         _lib.run("pob_linear_forward", m, k, n, _lib.ptr(x), x.stride(0) if m > 1 else max(x.stride(0), k),
                  _lib.ptr(wt), _lib.ptr(bias), _lib.ptr(residual), ldr if m > 1 else max(ldr, n), int(bool(relu)),
-                 _lib.ptr(out), n, _lib.current_stream(x.device),
+                 _lib.ptr(out), n, int(config), _lib.current_stream(x.device),
                  alg_bytes=4 * (m * k + k * n + m * n * (1 + (residual is not None)) + (n if bias is not None else 0)),
                  alg_flops=2 * m * k * n)
     return out

@@ -124,7 +124,7 @@ def invalidate_frozen(module: nn.Module) -> None:
 # Backend of the frozen linears.  "cublas": torch.addmm / _addmm_activation (cuBLAS SIMT GEMM, a cuBLASLt pass for
 # bias / ReLU, pob_affine_act for the skip); "pob": every linear runs pob_linear_forward (FP32 FFMA tiles, bias /
 # skip / ReLU applied on the accumulators); "auto" (default): pob_linear_forward where it measured faster on B200
-# (scratch/linear_time.py, profiles/): linears WITH an epilogue on >= 600 rows (one launch instead of two), the
+# (profiles/r01d_linear_time.txt): linears WITH an epilogue on >= 600 rows (one launch instead of two), the
 # 80 000-row layers, and shapes that are not 16-byte friendly; cuBLAS for the plain q/k/v GEMMs of the deeper stages.
 _LINEAR_BACKEND = os.environ.get("POINTOPS_B200_LINEAR", "auto")
 

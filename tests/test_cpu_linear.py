@@ -1,7 +1,7 @@
 """CPU-side checks around pob_linear_forward (csrc/linear.cu): no GPU here, so
   * the kernel's index arithmetic (k-major shared-memory staging, 4x4 / 8x4 / 8x8 register tiles, the intra-CTA
     split-K tree, ragged row / column tiles) is replayed thread by thread in numpy for every instantiated tile
-    configuration (scratch/linear_emulate.py is the transliteration of the kernel) and compared with float64;
+    configuration (a transliteration of the kernel) and compared with float64;
   * the per-shape backend policy of the frozen PTv1 form and the bench's one-JSON-line contract are exercised."""
 import importlib.util
 import json

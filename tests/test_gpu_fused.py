@@ -65,11 +65,7 @@ def test_pt_layer_forward_matches_torch(cuda, c, ns, tail, split):
     with torch.no_grad():
         ref = layer_reference(block.transformer, block.bn2 if tail else None, q, k, v, xyz, idx)
         f = block.frozen()
-        _lib.load().pob_pt_layer_set_split(split)
-        try:
-            out = FZ.pt_layer_forward(q, k, v, xyz, idx, f["params"], out_affine=tail)
-        finally:
-            _lib.load().pob_pt_layer_set_split(0)
+        out = FZ.pt_layer_forward(q, k, v, xyz, idx, f["params"], out_affine=tail, split=split)   # per-call option
     err = (out - ref).abs().max().item()
     assert err <= 1e-5 * max(ref.abs().max().item(), 1.0), err
 

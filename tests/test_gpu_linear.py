@@ -63,12 +63,7 @@ def test_every_tile_configuration_agrees(cuda, config, m, k, n):
     wt = torch.randn(k, n, device=cuda, generator=g) / k ** 0.5
     bias = torch.randn(n, device=cuda, generator=g)
     res = torch.randn(m, n, device=cuda, generator=g)
-    lib = _lib.load()
-    assert lib.pob_linear_set_config(config) == 0
-    try:
-        out = FZ.linear(x, wt, bias, res, True)
-    finally:
-        lib.pob_linear_set_config(0)
+    out = FZ.linear(x, wt, bias, res, True, config=config)   # per-call option: the library keeps no tuning state
     ref = reference(x, wt, bias, res, True)
     assert float((out.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
 

@@ -1,6 +1,6 @@
 """CPU simulation of the speculative-chain FPS protocol of csrc/fps.cu (fps_chain_kernel): checks that
 the emitted sequence equals plain FPS and reports the mean accepted chain length.
-python scratch/fps_chain_sim.py [n] [groups] [warps_per_group]"""
+python tools/fps_chain_sim.py [n] [groups] [warps_per_group]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

@@ -6,7 +6,7 @@ lists by key (value desc, index asc); the merged prefix is exactly the global FP
 entry is lowered by an earlier entry of ANOTHER group (pairwise point test) and no group's list has run
 out (terminal bound).  Checks equality with plain FPS and reports samples per exchange.
 
-python scratch/fps_merge_sim.py n W D_restart D_max [Kc] [m_limit]
+python tools/fps_merge_sim.py n W D_restart D_max [Kc] [m_limit]
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

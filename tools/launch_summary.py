@@ -1,5 +1,5 @@
 """Aggregate an ncu `--metrics gpu__time_duration.sum --csv` launch list by kernel name.
-python scratch/launch_summary.py launches.csv [rooms]"""
+python tools/launch_summary.py launches.csv [rooms]"""
 import csv, sys, re, collections
 rooms = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 rows = []
