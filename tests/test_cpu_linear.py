@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _emulator():
-    spec = importlib.util.spec_from_file_location("linear_emulate", os.path.join(ROOT, "scratch", "linear_emulate.py"))
+    spec = importlib.util.spec_from_file_location("linear_emulate", os.path.join(ROOT, "tools", "linear_emulate.py"))
     src = open(spec.origin).read().split("\ncfgs = [")[0]          # the functions only, not the sweep at the bottom
     mod = {}
     exec(compile(src, spec.origin, "exec"), mod)
