@@ -298,6 +298,19 @@ int pob_score_fused(int64_t n, int K, int b, const float* logits, const float* c
                     int* pred, float* ml_norm, float* scene_out, void* workspace, size_t workspace_bytes,
                     cudaStream_t stream);
 
+/* ----------------------------------------------------------- data path ----
+ * pob_grid_hash: GridSample's voxel coordinates and FNV64 key (pointcept/datasets/transform.py:813-823, 911-925):
+ * grid_coord (n, 3) i32 = floor(coord / grid_size) - min_cell (float64 division, as numpy does it), may be NULL;
+ * key (n) i64 = fnv_hash_vec(grid_coord) with the sign bit flipped, so that a signed sort orders it like numpy's
+ * unsigned argsort.  min_cell: device int64[3].
+ * pob_scatter_mean: torch_scatter.scatter_mean(src, index, dim=0, dim_size) as the tester averages fragment scores
+ * (pointcept/engines/test.py:243-248): out (dim_size, c) and count (dim_size) zeroed by the caller; rows whose index
+ * is outside [0, dim_size) are ignored.                                                                      */
+int pob_grid_hash(int64_t n, const float* coord, double gx, double gy, double gz, const long long* min_cell,
+                  int* grid_coord, long long* key, cudaStream_t stream);
+int pob_scatter_mean(int64_t rows, int c, const float* src, const long long* index, int64_t dim_size, float* out,
+                     float* count, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

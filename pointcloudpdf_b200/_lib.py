@@ -54,6 +54,8 @@ SIGNATURES = {
     "pob_attention_relation_step_backward": (I, [L, I, I, P, P, P, P, P, P, P, P, P, P]),
     "pob_attention_fusion_step_forward": (I, [L, I, I, P, P, P, P, P, P]),
     "pob_attention_fusion_step_backward": (I, [L, I, I, P, P, P, P, P, P, P, P]),
+    "pob_grid_hash": (I, [L, P, ctypes.c_double, ctypes.c_double, ctypes.c_double, P, P, P, P]),
+    "pob_scatter_mean": (I, [L, I, P, P, L, P, P, P]),
     "pob_score_workspace_bytes": (Z, [I]),
     "pob_score_fused": (I, [L, I, I, P, P, P, F, P, P, P, P, P, P, P, P, P, Z, P]),
 }

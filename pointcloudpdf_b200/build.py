@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpointops_b200.so")
-SOURCES = ["api.cu", "knn.cu", "fps.cu", "gather.cu", "score.cu", "ptlayer.cu", "attention.cu", "linear.cu"]
+SOURCES = ["api.cu", "knn.cu", "fps.cu", "gather.cu", "score.cu", "ptlayer.cu", "attention.cu", "linear.cu", "datapath.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]
 
