@@ -234,11 +234,23 @@ def cpu_port_points_per_sec(n_points: int, steps: int, warmup: int, threads: int
     """The reference's op sequence for the same workload on host cores: PTv1 Seg50 (literal path:
     kNN in every block, gather k and v, einsum) over the oracle's brute-force operators (C + OpenMP) + MSP.
     This is the one place bench.py executes oracle/ (cpu_baseline / --impl reference)."""
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm is meant to use all the host threads it can
+    os.environ["OMP_NUM_THREADS"] = str(threads)
     from oracle import pointops_oracle as O
     from pointcloudpdf_b200 import ptv1, synthetic as S
     import types
 
     torch.set_num_threads(threads)
+    O.lib()
+    try:   # the OpenMP runtime may have been initialised (with 1 thread) before the variable was changed
+        import ctypes
+        for name in ("libgomp.so.1", "libomp.so", "libiomp5.so"):
+            try:
+                ctypes.CDLL(name).omp_set_num_threads(int(threads))
+            except OSError:
+                pass
+    except Exception:   # noqa: BLE001
+        pass
     shim = types.SimpleNamespace(
         knn_query=lambda k, xyz, off, nx=None, noff=None: O.knn_query(k, xyz, off, nx, noff),
         farthest_point_sampling=O.farthest_point_sampling, grouping=O.grouping, aggregation=O.aggregation,

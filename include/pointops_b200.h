@@ -117,8 +117,9 @@ int pob_random_ball_query(int64_t m, int nsample, float min_radius, float max_ra
  * n_max = size of the largest scene (the reference's `n`); an over-estimate is allowed, an
  * under-estimate is not.  idx (new_offset[b-1]) i32 receives GLOBAL row indices, scene-major;
  * first sample of a scene is its first row; ties go to the lowest index.  tmp (n f32) needs no
- * initialisation and is only used when a scene exceeds the register-resident capacity
- * (131072 points); it may be NULL below that.  cluster_hint: 0 = auto, or 1/2/4/8/16 CTAs per
+ * initialisation and is only used (as scratch of the grid-wide / streamed forms) when a scene exceeds what one
+ * 16-CTA cluster holds (196608 points with the merged-list kernel, 131072 with variants 2 / 3); it may be NULL
+ * below 131072.  cluster_hint: 0 = auto, or 1/2/4/8/16 CTAs per
  * scene.  A scene requesting 0 samples writes nothing (reference quirk C5 not reproduced).
  * grid_workspace (optional, else NULL): the workspace pob_knn_grid_build filled for the same
  * xyz / offset, with its n (rows of xyz) and cell_pts; the kernel then walks the points in cell

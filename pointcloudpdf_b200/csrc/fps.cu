@@ -817,6 +817,10 @@ static int launch_merge(int P, int b, int C, cudaStream_t stream, void** args) {
     POB_FPS_CASE(6, fps_merge_kernel); POB_FPS_CASE(8, fps_merge_kernel);
     POB_FPS_CASE(12, fps_merge_sp_kernel); POB_FPS_CASE(16, fps_merge_sp_kernel); POB_FPS_CASE(20, fps_merge_sp_kernel);
     POB_FPS_CASE(24, fps_merge_sp_kernel); POB_FPS_CASE(32, fps_merge_sp1_kernel);
+    // beyond 32 points per thread the coordinates only fit in shared memory (16 B x 256 x 48 = 196 KB) and two rows share
+    // a pruning box: scenes of 131 073 .. 196 608 points (most ScanNet scenes) still run inside ONE cluster, whose round is
+    // a third of the grid-wide form's
+    POB_FPS_CASE(40, fps_merge_sp1_kernel); POB_FPS_CASE(48, fps_merge_sp1_kernel);
 #undef POB_FPS_CASE
     return POB_ERR_UNSUPPORTED;
 }
@@ -880,7 +884,9 @@ POB_API int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, 
         sorted = (const float4*)(ws + L.off_sorted);
     }
     constexpr int T = 256;      // 2 warps per scheduler: the per-iteration overhead scales with warps
-    constexpr int PMAX = 32;    // registers: 5 per point + ~50
+    // points per thread: 32 with the coordinates in registers (round-1 kernels), 48 for the merged-list kernel with
+    // its coordinates in shared memory
+    const int PMAX = variant <= 1 ? 48 : 32;
     int C = cluster_hint;
     if (C != 1 && C != 2 && C != 4 && C != 8 && C != 16) {
         if (variant != 3) {
@@ -896,7 +902,7 @@ POB_API int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, 
     while (C < 16 && ceil_div(n_max, (int64_t)C * T) > PMAX) C *= 2;
     const int64_t P = ceil_div(n_max, (int64_t)C * T);
     constexpr int FPS_D = 2, FPS_KC = 4;
-    if (P > PMAX && variant <= 1 && n_max <= (int64_t)sm_count() * T * PMAX) {
+    if (P > PMAX && variant <= 1 && n_max <= (int64_t)sm_count() * T * 32) {
         // beyond one cluster's registers: the grid-wide form, one cooperative launch per scene (a scene that fits a
         // cluster returns at once there and is sampled by the cluster launch below, and vice versa).  Workspace in
         // tmp: a counter (zeroed here) and the message buffers.

@@ -110,15 +110,20 @@ __device__ __forceinline__ unsigned fps_row_mask(const float (&rlo)[3], const fl
     (SP ? [&] { const float4 q_ = warp_pts[(p) * 32 + lane]; return d2_ref(q_.x, q_.y, q_.z, sx, sy, sz); }() \
         : d2_ref(px[SP ? 0 : (p)], py[SP ? 0 : (p)], pz[SP ? 0 : (p)], sx, sy, sz))
 
-// for every row p whose bit is set in `mask` (warp-uniform): BODY with the compile-time index p; rows are skipped
-// four at a time
-#define POB_FPS_FOR_ROWS(mask, BODY)                                            \
-    _Pragma("unroll") for (int g_ = 0; g_ < P; g_ += 4) {                       \
-        if ((mask) & (0xFu << g_)) {                                            \
-            _Pragma("unroll") for (int p = g_; p < (g_ + 4 < P ? g_ + 4 : P); p++) { \
-                if ((mask) & (1u << p)) { BODY }                                \
-            }                                                                   \
-        }                                                                       \
+// for every row p covered by a set bit of `mask` (warp-uniform; bit b covers the RG consecutive rows b*RG .. b*RG+RG-1):
+// BODY with the compile-time index p; bits are skipped four at a time.  NB = number of bits = P / RG.
+#define POB_FPS_FOR_ROWS(mask, BODY)                                                          \
+    _Pragma("unroll") for (int g_ = 0; g_ < NB; g_ += 4) {                                    \
+        if ((mask) & (0xFu << g_)) {                                                          \
+            _Pragma("unroll") for (int b_ = g_; b_ < (g_ + 4 < NB ? g_ + 4 : NB); b_++) {     \
+                if ((mask) & (1u << b_)) {                                                    \
+                    _Pragma("unroll") for (int r_ = 0; r_ < RG; r_++) {                       \
+                        const int p = b_ * RG + r_;                                           \
+                        BODY                                                                  \
+                    }                                                                         \
+                }                                                                             \
+            }                                                                                 \
+        }                                                                                     \
     }
 
 // One cluster of C CTAs (T = 256 threads) per scene; P points per thread in registers; D list entries per warp;
@@ -152,6 +157,10 @@ fps_merge_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
     constexpr int ME = KC + 1;                 // entries per CTA message (KC + its terminal)
     constexpr int NSLOT = FPS_MAX_CLUSTER * ME;
     constexpr int LMAX = 32;                   // samples accepted per exchange, at most
+    constexpr int RG = P > 32 ? 2 : 1;         // rows per pruning box (one box per lane: P / RG <= 32 boxes)
+    constexpr int NB = P / RG;
+    static_assert(P % RG == 0 && NB <= 32, "one row box per lane");
+    constexpr unsigned ALLROWS = NB < 32 ? (1u << NB) - 1u : FULL;
     static_assert(T == 256, "the pair test maps 256 threads onto 32 x 8 (j, i mod 8)");
     static_assert((NW & (NW - 1)) == 0 && WL * NW <= 32 && CE >= ME, "CTA ranking: NW lanes per warp-list entry");
     static_assert(NSLOT % NW == 0 && NSLOT / NW <= 32, "cluster ranking: each warp ranks NSLOT / NW entries");
@@ -187,8 +196,8 @@ fps_merge_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
     constexpr int PR = SP ? 1 : P;
     float px[PR], py[PR], pz[PR], pt[P], st[P];
     float blo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, bhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    // second pruning level: lane p < P keeps the bounding box of ROW p = the 32 consecutive points (one per lane)
-    // of register slot p -- in cell order that is a patch of a few cells, far tighter than the warp's box
+    // second pruning level: lane b < NB keeps the bounding box of rows b*RG .. b*RG+RG-1, a ROW being the 32 consecutive
+    // points (one per lane) of a register slot -- in cell order a patch of a few cells, far tighter than the warp's box
     float rlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, rhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     bool box_ok = true;
     const int sbase = in_cells ? __ldg(cell_start + scenes[scene].cell_base) : 0;
@@ -230,9 +239,9 @@ fps_merge_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
                     h3[a] = fmaxf(h3[a], __shfl_xor_sync(FULL, h3[a], o));
                 }
             }
-            if (lane == p) {
+            if (lane == p / RG) {
 #pragma unroll
-                for (int a = 0; a < 3; a++) { rlo[a] = l3[a]; rhi[a] = h3[a]; }
+                for (int a = 0; a < 3; a++) { rlo[a] = fminf(rlo[a], l3[a]); rhi[a] = fmaxf(rhi[a], h3[a]); }
             }
         }
     }
@@ -349,8 +358,7 @@ fps_merge_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
                 const bool foreign = (fm >> j) & 1u;
                 tm &= tm - 1;
                 const float4 s = reinterpret_cast<const float4*>(&s_sorted[j])[1];
-                const unsigned rmask = (prune && !first) ? fps_row_mask<P>(rlo, rhi, s.x, s.y, s.z, wmaxf, lane)
-                                                         : (P < 32 ? (1u << P) - 1u : FULL);
+                const unsigned rmask = (prune && !first) ? fps_row_mask<NB>(rlo, rhi, s.x, s.y, s.z, wmaxf, lane) : ALLROWS;
                 if (foreign) {
                     lowered = lowered || d2_ref(wx, wy, wz, s.x, s.y, s.z) < wv;
                     POB_FPS_FOR_ROWS(rmask, {
@@ -361,7 +369,7 @@ fps_merge_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
                 } else {
                     POB_FPS_FOR_ROWS(rmask, { pt[p] = fminf(POB_FPS_D2(p, s.x, s.y, s.z), pt[p]); })
                 }
-                if (stats) n_evals += 32u * (unsigned)__popc(rmask);
+                if (stats) n_evals += 32u * RG * (unsigned)__popc(rmask);
             }
             const unsigned lm = __ballot_sync(FULL, lowered);
             const bool restart = first || (lm & ((1u << len) - 1u)) != 0u;   // a pending entry was lowered: the list is void
@@ -381,10 +389,9 @@ fps_merge_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
                 if (lane == 0) ent_store(my_wl + len, make_ent(nb, ni, nx, ny, nz, gw, !(nb == 0u && len > 0)));
                 len++;
                 {   // nb is the maximum of st: rows farther than that from the new local sample cannot change
-                    const unsigned rmask = prune ? fps_row_mask<P>(rlo, rhi, nx, ny, nz, __uint_as_float(nb), lane)
-                                                 : (P < 32 ? (1u << P) - 1u : FULL);
+                    const unsigned rmask = prune ? fps_row_mask<NB>(rlo, rhi, nx, ny, nz, __uint_as_float(nb), lane) : ALLROWS;
                     POB_FPS_FOR_ROWS(rmask, { st[p] = fminf(POB_FPS_D2(p, nx, ny, nz), st[p]); })
-                    if (stats) n_evals += 32u * (unsigned)__popc(rmask);
+                    if (stats) n_evals += 32u * RG * (unsigned)__popc(rmask);
                 }
                 fps_warp_argmax<P>(st, warp_pts, lane, nb, ni, nx, ny, nz);
             }

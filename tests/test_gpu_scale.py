@@ -118,10 +118,12 @@ def test_fps_large_scene_thousands_of_samples(cuda, oracle, n, m, kind):
     assert torch.equal(out.cpu(), ref)
 
 
-def test_fps_large_scene_in_a_batch_with_small_ones(cuda, oracle):
+@pytest.mark.parametrize("sizes,ms", [([180_000, 3000, 40_000], [2500, 750, 2000]),      # one cluster each (48 points per thread)
+                                      ([230_000, 3000, 150_000], [2000, 750, 1500])])     # grid-wide + two cluster scenes in one call
+def test_fps_large_scene_in_a_batch_with_small_ones(cuda, oracle, sizes, ms):
     import pointops
-    xyz, offset = room([180_000, 3000, 40_000], 2033)
-    new_offset = torch.tensor([2500, 2500 + 750, 2500 + 750 + 2000], dtype=torch.int32)
+    xyz, offset = room(sizes, 2033)
+    new_offset = torch.tensor(np.cumsum(ms), dtype=torch.int32)
     ref = oracle.farthest_point_sampling(xyz, offset, new_offset)
     out = pointops.farthest_point_sampling(xyz.to(cuda), offset.to(cuda), new_offset.to(cuda))
     assert torch.equal(out.cpu(), ref)
