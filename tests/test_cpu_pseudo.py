@@ -52,3 +52,17 @@ def test_ball_query_partial_dense_oracle_semantics():
     idx, d2 = PO.ball_query_partial_dense(0.1, 2, x, x, batch, batch)
     assert idx.tolist() == [[0, 1], [0, 1], [2, -1], [0, 1], [4, 5], [4, 5]]     # first two IN INDEX ORDER, own scene only
     assert d2[2].tolist() == [0.0, -1.0]
+
+
+def test_tp_compat_surface_and_no_cpu_path():
+    """The stand-in for `import torch_points_kernels as tp` serves exactly the call the recognizer makes and nothing else;
+    CPU tensors are rejected (no CPU path)."""
+    from pointcloudpdf_b200 import tp_compat
+    x = torch.rand(32, 3)
+    b = torch.zeros(32, dtype=torch.long)
+    with pytest.raises(NotImplementedError):
+        tp_compat.ball_query(0.1, 8, x, x, mode="dense")
+    with pytest.raises(NotImplementedError):
+        tp_compat.ball_query(0.1, 8, x, x, mode="partial_dense", batch_x=b, batch_y=b, sort=True)
+    with pytest.raises(ValueError):
+        tp_compat.ball_query(0.1, 8, x, x, mode="partial_dense", batch_x=b, batch_y=b)

@@ -26,7 +26,7 @@ from pointcloudpdf_b200 import _lib, synthetic as S  # noqa: E402
 import pointcloudpdf_b200.pointops as pointops  # noqa: E402
 
 dev = torch.device("cuda:0")
-lib = _lib.load()
+lib = _lib.load() if torch.cuda.is_available() else None
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libpointops_ref.so")
 ref = ctypes.CDLL(REF_SO) if os.path.exists(REF_SO) else None
 try:
