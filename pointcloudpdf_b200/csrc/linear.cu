@@ -206,6 +206,159 @@ linear_tile_kernel(int64_t M, int K, int N, int col_tiles, const float* __restri
                    make_float4(acc[i][h * 4], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core form (round 2): the same contract on mma.sync m16n8k8 TF32 with the "3xTF32" split, which keeps the
+// result f32-accurate: every f32 operand is split a = a_hi + a_lo with a_hi = tf32(a), a_lo = tf32(a - a_hi), and
+//      a * b  ~=  a_lo * b_hi + a_hi * b_lo + a_hi * b_hi          (the dropped a_lo * b_lo is ~2^-22 relative)
+// is accumulated in f32 -- measured error vs float64 ~5e-7 of the largest output, against ~1e-7 for FFMA and ~1e-3 for
+// plain TF32 (which the parity bars of this path exclude).  Why: these linears are short, skinny GEMMs (0.16 - 0.5 GFLOP,
+// K up to 512) whose FFMA k-loop is 1 000 dependent issue slots per 32-wide k-tile and thread; three MMAs per 16 x 8 x 8
+// block replace 128 FFMAs per lane, so the k-loop is bound by the shared-memory fragment loads instead, and the 80 000-row
+// layers become memory-bound.  (tcgen05 / TMEM would be the Blackwell form of a LARGE contraction; at a quarter GFLOP
+// per launch the launch and the k-loop latency decide, and warp-level MMA needs no TMEM allocation, descriptors or TMA
+// maps per launch.)
+// CTA tile BM x BN, WM x WN warps, k-tiles of 32 staged by cp.async (16-byte, zero-filled tails) into padded shared
+// memory: As[m][32 + 4] and Bs[k][BN + 8] make every fragment load conflict-free.  Epilogue on the accumulators.
+__device__ __forceinline__ unsigned f2tf32(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+template <int BM, int BN, int WM, int WN, int STAGES>
+__global__ void __launch_bounds__(WM * WN * 32)
+linear_mma_kernel(int64_t M, int K, int N, int col_tiles, const float* __restrict__ A, int64_t lda,
+                  const float* __restrict__ Wt, const float* __restrict__ bias, const float* __restrict__ residual,
+                  int64_t ldr, int relu, float* __restrict__ out, int64_t ldo) {
+    constexpr int BK = 32, NT = WM * WN * 32;
+    constexpr int TM = BM / WM, TN = BN / WN;          // warp tile
+    constexpr int MT = TM / 16, NTL = TN / 8;          // MMA tiles per warp
+    constexpr int AS = BK + 4, BS = BN + 8;
+    constexpr int STAGE_FLOATS = BM * AS + BK * BS;
+    static_assert(TM % 16 == 0 && TN % 8 == 0 && STAGES >= 2, "warp tile is a multiple of 16 x 8");
+    extern __shared__ __align__(16) float lin_smem[];   // [STAGES][BM * AS + BK * BS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / WN, wn = warp % WN;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t m0 = (int64_t)(blockIdx.x / col_tiles) * BM;
+    const int n0 = (int)(blockIdx.x % col_tiles) * BN;
+    const int tiles = (K + BK - 1) / BK;
+
+    // STAGES - 1 k-tiles are in flight while one is multiplied.  Two stages is what is instantiated: deeper pipelines
+    // were measured no faster (the deep shapes wait on the dependent MMA chain, not on memory) and cost CTAs per SM.
+    auto load_tile = [&](int kt) {
+        if (kt < tiles) {
+            float* as = lin_smem + (kt % STAGES) * STAGE_FLOATS;
+            float* bs = as + BM * AS;
+            const int k0 = kt * BK;
+            for (int c = tid; c < BM * (BK / 4); c += NT) {
+                const int row = c / (BK / 4), kq = c % (BK / 4);
+                const int64_t gm = m0 + row;
+                const int gk = k0 + kq * 4;
+                const int bytes = (gm < M && gk < K) ? min(16, (K - gk) * 4) : 0;
+                cp_async16(as + row * AS + kq * 4, A + (gm < M ? gm : 0) * lda + (gk < K ? gk : 0), bytes);
+            }
+            for (int c = tid; c < BK * (BN / 4); c += NT) {
+                const int kk = c / (BN / 4), nq = c % (BN / 4);
+                const int gk = k0 + kk, gn = n0 + nq * 4;
+                const int bytes = (gk < K && gn < N) ? min(16, (N - gn) * 4) : 0;
+                cp_async16(bs + kk * BS + nq * 4, Wt + (int64_t)(gk < K ? gk : 0) * N + (gn < N ? gn : 0), bytes);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");   // an empty group keeps the wait arithmetic uniform
+    };
+
+    float acc[MT][NTL][4];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NTL; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) load_tile(s);
+    for (int kt = 0; kt < tiles; ++kt) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");   // tile kt has landed
+        __syncthreads();                      // ... for everyone, and tile kt - 1 is no longer being read
+        load_tile(kt + STAGES - 1);           // into the buffer of tile kt - 1
+        const float* a = lin_smem + (kt % STAGES) * STAGE_FLOATS + (wm * TM) * AS;
+        const float* b = lin_smem + (kt % STAGES) * STAGE_FLOATS + BM * AS + wn * TN;
+#pragma unroll
+        for (int k8 = 0; k8 < BK; k8 += 8) {
+            unsigned ah[MT][4], al[MT][4], bh[NTL][2], bl[NTL][2];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                const float* ap = a + (i * 16 + g) * AS + k8 + t;
+                const float v[4] = {ap[0], ap[8 * AS], ap[4], ap[8 * AS + 4]};   // (g, t) (g+8, t) (g, t+4) (g+8, t+4)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    ah[i][r] = f2tf32(v[r]);
+                    al[i][r] = f2tf32(v[r] - __uint_as_float(ah[i][r]));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NTL; ++j) {
+                const float* bp = b + (k8 + t) * BS + j * 8 + g;
+                const float v[2] = {bp[0], bp[4 * BS]};                             // (k = t, n = g) (k = t + 4, n = g)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    bh[j][r] = f2tf32(v[r]);
+                    bl[j][r] = f2tf32(v[r] - __uint_as_float(bh[j][r]));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NTL; ++j) {
+                    mma_tf32(acc[i][j], al[i], bh[j]);    // small terms first
+                    mma_tf32(acc[i][j], ah[i], bl[j]);
+                    mma_tf32(acc[i][j], ah[i], bh[j]);
+                }
+        }
+    }
+
+    // epilogue: accumulator r of MMA tile (i, j) is row (g + 8 * (r / 2)), column (2 * t + r % 2)
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NTL; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t gm = m0 + wm * TM + i * 16 + g + 8 * h;
+                const int gn = n0 + wn * TN + j * 8 + 2 * t;
+                if (gm >= M || gn >= N) continue;   // N % 4 == 0 on this path: a column pair is inside or outside together
+                float2 v = make_float2(acc[i][j][2 * h], acc[i][j][2 * h + 1]);
+                if (bias) { const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + gn)); v.x += bb.x; v.y += bb.y; }
+                if (residual) { const float2 rr = __ldg(reinterpret_cast<const float2*>(residual + gm * ldr + gn)); v.x += rr.x; v.y += rr.y; }
+                if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+                *reinterpret_cast<float2*>(out + gm * ldo + gn) = v;
+            }
+}
+
+template <int BM, int BN, int WM, int WN, int STAGES>
+static int launch_linear_mma(int64_t M, int K, int N, const float* A, int64_t lda, const float* Wt, const float* bias,
+                             const float* residual, int64_t ldr, int relu, float* out, int64_t ldo, cudaStream_t stream) {
+    const int col_tiles = (N + BN - 1) / BN;
+    const int64_t ctas = ((M + BM - 1) / BM) * col_tiles;
+    if (ctas > 0x7fffffffLL) return POB_ERR_UNSUPPORTED;
+    constexpr size_t smem = sizeof(float) * STAGES * (BM * (32 + 4) + 32 * (BN + 8));
+    auto kern = linear_mma_kernel<BM, BN, WM, WN, STAGES>;
+    if (smem > 48 * 1024) POB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: every launch
+    kern<<<(unsigned)ctas, WM * WN * 32, smem, stream>>>(M, K, N, col_tiles, A, lda, Wt, bias, residual, ldr, relu, out, ldo);
+    pob_count_launches(1);
+    POB_RETURN_LAST_ERROR();
+}
+
 static inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <int BM, int BN, int BK, int KS, int TM, int TN>
@@ -248,7 +401,8 @@ static int launch_linear_unaligned(int64_t M, int K, int N, bool vec_k, bool vec
 
 using namespace pob;
 
-#define POB_LINEAR_CONFIGS 16   // `config` (per call): 0 = pick the tile from the shape; 1..16 = force one (tests, tuning)
+#define POB_LINEAR_CONFIGS 21   // `config` (per call): 0 = pick from the shape; 1..16 = force an FFMA tile, 17..20 = a tensor-core
+                                // (3xTF32) tile, 21 = the FFMA tile the shape would pick (tests, tuning, A/B)
 
 // Tile choice, from the per-shape timings on B200 (profiles/r01d_linear_time.txt): the shapes are skinny
 // and small (0.16-0.5 GFLOP), so a launch is latency bound -- what matters is >= ~2 CTAs per SM with as many
@@ -280,7 +434,20 @@ POB_API int pob_linear_forward(int64_t M, int K, int N, const float* A, int64_t 
                        (!residual || (ldr % 4 == 0 && al16p(residual)));
     if (!(vec_k && vec_n))
         return launch_linear_unaligned(M, K, N, vec_k, vec_n, A, lda, Wt, bias, residual, ldr, relu, out, ldo, stream);
-    const int cfg = g_linear_force ? g_linear_force : pick_linear_config(M, K, N);
+    // default (gpurun_out/r02_linear_time.json): the tensor-core (3xTF32) form for the long, residual-free shapes --
+    // there the legacy HMMA path (about the A100 TF32 rate per SM, so 3 MMAs per product buy ~1.3x over FFMA at best)
+    // is 10-30 % ahead; the short, deep shapes are bound by the launch and the dependent chain over K, where the
+    // split-K FFMA tiles below are as fast or faster.
+    int cfg = g_linear_force;
+    if (cfg == 0) cfg = (M >= 10000 && !residual && N % 32 == 0) ? (N == 32 ? 17 : (N == 96 ? 18 : 19)) : 21;
+    if (cfg == 21) cfg = pick_linear_config(M, K, N);
+    switch (cfg) {
+        case 17: return launch_linear_mma<128, 32, 4, 1, 2>(M, K, N, A, lda, Wt, bias, residual, ldr, relu, out, ldo, stream);
+        case 18: return launch_linear_mma<64, 96, 2, 3, 2>(M, K, N, A, lda, Wt, bias, residual, ldr, relu, out, ldo, stream);   // q/k/v: N = 3C
+        case 19: return launch_linear_mma<64, 64, 2, 2, 2>(M, K, N, A, lda, Wt, bias, residual, ldr, relu, out, ldo, stream);
+        case 20: return launch_linear_mma<32, 32, 2, 2, 2>(M, K, N, A, lda, Wt, bias, residual, ldr, relu, out, ldo, stream);
+        default: break;
+    }
 #define POB_LINEAR_CASE(ID, BM, BN, BK, KS, TM, TN) \
     case ID: return launch_linear<BM, BN, BK, KS, TM, TN>(M, K, N, A, lda, Wt, bias, residual, ldr, relu, out, ldo, stream)
     switch (cfg) {

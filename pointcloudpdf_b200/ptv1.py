@@ -145,6 +145,8 @@ def _use_pob_linear(m: int, k: int, n: int, epilogue: bool) -> bool:
         return True
     if m >= 40000:
         return n <= 96
+    if m >= 10000 and n <= 192:
+        return True          # 3xTF32 tensor-core tiles: 15.2 vs 18.7 us (cuBLAS) at 20 000 x 64 x 192
     return epilogue and m >= 600
 
 

@@ -51,6 +51,7 @@ def test_backend_policy():
         ptv1.set_linear_backend("auto")
         assert ptv1._use_pob_linear(80000, 6, 32, True)          # not 16-byte friendly -> only pob handles it in one launch
         assert ptv1._use_pob_linear(80000, 32, 96, False)        # 80 000-row layers
+        assert ptv1._use_pob_linear(20000, 64, 192, False)       # tensor-core (3xTF32) tiles beat cuBLAS's f32 GEMM there
         assert ptv1._use_pob_linear(5000, 128, 128, True)        # epilogue: one launch instead of two
         assert not ptv1._use_pob_linear(5000, 128, 384, False)   # plain q/k/v of the deeper stages: cuBLAS
         assert not ptv1._use_pob_linear(312, 512, 512, True)

@@ -51,10 +51,11 @@ def test_linear_matches_float64(cuda, m, k, n, epilogue):
     assert float((out.double() - ref).abs().max()) <= 1e-5 * scale
 
 
-@pytest.mark.parametrize("config", list(range(1, 17)))
+@pytest.mark.parametrize("config", list(range(1, 22)))
 @pytest.mark.parametrize("m,k,n", [(700, 64, 96), (130, 8, 12), (33, 512, 136)])
 def test_every_tile_configuration_agrees(cuda, config, m, k, n):
-    """The tile is normally picked from the shape; forced here so that each instantiation (4x4 / 8x4 / 8x8
+    """Configurations 1-16 are the FFMA tiles, 17-20 the tensor-core (3xTF32) tiles, 21 the FFMA tile the shape would pick.
+    The tile is normally picked from the shape; forced here so that each instantiation (4x4 / 8x4 / 8x8
     register tiles, split-K 1..8 with its reduction tree) sees ragged rows, ragged columns and short K."""
     from pointcloudpdf_b200 import _lib
     from pointcloudpdf_b200.pointops import fused as FZ
@@ -107,3 +108,24 @@ def test_frozen_model_same_logits_on_both_linear_backends(cuda):
     c = outs["cublas"]
     for name in ("pob", "auto"):
         assert float((outs[name] - c).abs().max()) <= 1e-4 * max(1.0, float(c.abs().max())), name
+
+
+@pytest.mark.parametrize("m,k,n", [(80000, 32, 96), (20000, 64, 64), (5000, 128, 384), (1250, 256, 768), (312, 512, 1536), (312, 512, 256)])
+def test_tensor_core_form_is_f32_accurate(cuda, m, k, n):
+    """3xTF32: error against float64 within 1e-5 of the largest output (the bar of every linear test), and within a few f32
+    ulps of the FFMA form -- NOT the 1e-3 of plain TF32 (which the parity bars of this path exclude)."""
+    from pointcloudpdf_b200.pointops import fused as FZ
+    g = torch.Generator(device=cuda).manual_seed(m + k + n)
+    x = torch.randn(m, k, device=cuda, generator=g) * 3
+    wt = torch.randn(k, n, device=cuda, generator=g) / k ** 0.5
+    bias = torch.randn(n, device=cuda, generator=g)
+    res = torch.randn(m, n, device=cuda, generator=g)
+    ref = torch.relu(x.double() @ wt.double() + bias.double() + res.double())
+    scale = float(ref.abs().max())
+    mma = FZ.linear(x, wt, bias, res, True, config=0)
+    ffma = FZ.linear(x, wt, bias, res, True, config=21)
+    err_mma = float((mma.double() - ref).abs().max()) / scale
+    err_ffma = float((ffma.double() - ref).abs().max()) / scale
+    assert err_mma <= 5e-6 and err_ffma <= 2e-6, (err_mma, err_ffma)
+    tf32 = torch.relu((x.double().float().to(torch.float32)) @ wt + bias + res)   # what one TF32 pass would cost, for the record
+    assert float((mma - ffma).abs().max()) <= 6e-6 * scale
