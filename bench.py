@@ -331,6 +331,43 @@ def gpu_reference_before(n_points: int, steps: int = 3):
             out[key] = {"value": n_points / sec, "unit": UNIT, "ms_per_step": sec * 1e3, "timed_steps": len(times)}
         except Exception as e:   # noqa: BLE001 -- a context number must never take the arm down
             out[key] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    # ---- the same comparison for a cfg3 training step (8 ScanNet-shaped scenes, fwd + bwd + SGD, f32) ----
+    g = torch.Generator().manual_seed(2027)
+    sizes = [int(x) for x in torch.randint(90000, 100001, (8,), generator=g)]
+    tb = S.scannet_batch(sizes, seed=2027)
+    td = {k: tb[k].to(dev) for k in ("coord", "feat", "offset")}
+    label = torch.randint(0, 20, (td["coord"].shape[0],), device=dev, generator=torch.Generator(device=dev).manual_seed(2027))
+    train = {}
+    for backend, key in (("refgpu", "reference_kernels"), ("product", "dropin_kernels_unmodified_callers")):
+        if backend == "refgpu" and not os.path.exists(ref_glue.REF_SO):
+            train[key] = {"unavailable": "oracle/_ref/libpointops_ref.so not built"}
+            continue
+        try:
+            with ref_glue.reference_modules(backend) as R:
+                torch.manual_seed(2024)
+                model = R.ptseg.PointTransformerSeg50(in_channels=9, num_classes=20).to(dev).train()
+                opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9)
+                times = []
+                for i in range(1 + 2):
+                    if backend == "product":
+                        R.pointops.clear_caches()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    opt.zero_grad(set_to_none=True)
+                    torch.nn.functional.cross_entropy(model(dict(td)), label).backward()
+                    opt.step()
+                    torch.cuda.synchronize()
+                    if i >= 1:
+                        times.append(time.perf_counter() - t0)
+                del model, opt
+            sec = statistics.median(times)
+            train[key] = {"points_per_sec": sum(sizes) / sec, "ms_per_step": sec * 1e3, "timed_steps": len(times)}
+        except Exception as e:   # noqa: BLE001
+            train[key] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
+    train["what"] = ("BASELINE configs[2] on one GPU: the unmodified PointTransformerSeg50 in train mode, 8 ScanNet-shaped scenes "
+                     "(%d points), forward + cross-entropy + backward + SGD step, f32, eager, wall clock around synchronize" % sum(sizes))
+    out["cfg3_training_step"] = train
     out["what"] = ("unmodified point_transformer_seg.py + max_probability_v1m1_base.py, eval, f32, one 80 000-point room per step, "
                    "eager launches on the legacy default stream, wall clock around synchronize; `reference_kernels` = the "
                    "reference's libs/pointops .cu files compiled unmodified for sm_100a (the GPU 'before'), "
@@ -470,11 +507,14 @@ def ops_cfg1(dev, hbm_peak):
 
 # ------------------------------------------------------- the other partitioned workloads --
 
-def cfg3_training(dev, rank, world, dist):
+def cfg3_training(dev, rank, world, dist, amp=False):
     """BASELINE configs[2]: PTv1 ScanNet20-shaped training step, 8 scenes x ~95k points, scene-sharded 8/N per
     rank, DistributedDataParallel (bucketed NCCL all-reduce overlapped with backward, broadcast_buffers=False,
     as pointcept/engines/defaults.py:22-43 / train.py:218-222), cross-entropy, SGD.  Strong scaling: the batch is
-    fixed; rank 0 also times the whole batch alone (no DDP) in the same process for the 1-GPU base."""
+    fixed; rank 0 also times the whole batch alone (no DDP) in the same process for the 1-GPU base.
+    amp: the step as the shipped configs run it (enable_amp = True, configs/scannet/semseg-pt-v1-0-base.py:7):
+    forward and loss under torch.autocast(float16), GradScaler around backward / step (engines/train.py:196-216);
+    the pointops kernels still see f32 coordinates and compute in f32."""
     from pointcloudpdf_b200 import synthetic as S, sharding
     from pointcloudpdf_b200.ptv1 import PointTransformerSeg50
     import pointcloudpdf_b200.pointops as pointops
@@ -512,15 +552,23 @@ def cfg3_training(dev, rank, world, dist):
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], broadcast_buffers=False,
                                                           gradient_as_bucket_view=True)
 
+    scaler = torch.amp.GradScaler("cuda", enabled=amp)
+
+    def fwd_bwd(m, dd, oh, lab):
+        with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+            loss = torch.nn.functional.cross_entropy(m(dd, oh), lab)
+        scaler.scale(loss).backward()
+
     def step(sync=True):
         pointops.clear_caches()
         opt.zero_grad(set_to_none=True)
         if world > 1 and not sync:
             with model.no_sync():
-                torch.nn.functional.cross_entropy(model(d, off_host), label).backward()
+                fwd_bwd(model, d, off_host, label)
         else:
-            torch.nn.functional.cross_entropy(model(d, off_host), label).backward()
-        opt.step()
+            fwd_bwd(model, d, off_host, label)
+        scaler.step(opt)
+        scaler.update()
 
     torch.cuda.reset_peak_memory_stats()
     ms = timed(step)
@@ -535,7 +583,8 @@ def cfg3_training(dev, rank, world, dist):
            "ms_per_step_without_allreduce": ms_nosync, "allreduce_exposed_ms": max(ms - ms_nosync, 0.0),
            "allreduce": "torch DistributedDataParallel over NCCL: 25 MB buckets, all-reduce launched from autograd hooks while "
                         "backward is still running (overlapped); gradient_as_bucket_view, broadcast_buffers=False" if world > 1 else "none (1 GPU)",
-           "what": "forward + backward (autograd through every pointops kernel) + gradient all-reduce + SGD step, f32, "
+           "precision": "autocast(float16) + GradScaler, as enable_amp = True in the shipped configs" if amp else "f32 (TF32 off)",
+           "what": "forward + backward (autograd through every pointops kernel) + gradient all-reduce + SGD step, "
                    "max over ranks of the median of 3 steps"}
     if world > 1:
         del model
@@ -547,8 +596,9 @@ def cfg3_training(dev, rank, world, dist):
             def step1():
                 pointops.clear_caches()
                 opt.zero_grad(set_to_none=True)
-                torch.nn.functional.cross_entropy(net(d, off_host), label).backward()
-                opt.step()
+                fwd_bwd(net, d, off_host, label)
+                scaler.step(opt)
+                scaler.update()
             base_ms = timed(step1, warm=1, reps=3, sync_ranks=False)
         bt = torch.tensor([base_ms or 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(bt, op=dist.ReduceOp.MAX)
@@ -823,6 +873,10 @@ def main():
             multi["cfg3_training"] = cfg3_training(dev, rank, world, dist)
         except Exception as e:   # noqa: BLE001 -- a side workload must not take the headline line down
             multi["cfg3_training"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        try:
+            multi["cfg3_training_amp"] = cfg3_training(dev, rank, world, dist, amp=True)
+        except Exception as e:   # noqa: BLE001
+            multi["cfg3_training_amp"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         try:
             multi["cfg5_sharded_knn"] = cfg5_sharded_knn(dev, rank, world, dist)
         except Exception as e:   # noqa: BLE001
