@@ -85,14 +85,23 @@ def run_shape(tag, n, k, c, wc):
     B = 4
     rows = {}
 
+    def copy_floor(nbytes):
+        """A plain device copy moving the same number of bytes (half read, half written), timed the same way: what a
+        launch of this size can reach at all -- the fixed cost of a launch is 2-3 us, a third of the small rows."""
+        half = max(4, nbytes // 8 * 4)
+        bufs = [(torch.empty(half // 4, device=dev), torch.empty(half // 4, device=dev)) for _ in range(NSETS)]
+        return time_graph(lambda a: bufs[a][1].copy_(bufs[a][0]))
+
     def row(name, nbytes, mine, theirs=None):
         us = time_graph(mine)
-        r = {"b200_us": us, "alg_MB": nbytes / 1e6, "b200_GBps": nbytes / us / 1e3, "b200_frac_of_hbm_peak": nbytes / us / 1e3 / HBM}
+        cu = copy_floor(nbytes)
+        r = {"b200_us": us, "alg_MB": nbytes / 1e6, "b200_GBps": nbytes / us / 1e3, "b200_frac_of_hbm_peak": nbytes / us / 1e3 / HBM,
+             "same_bytes_copy_us": cu, "b200_frac_of_copy_speed": cu / us}
         if theirs is not None and ref is not None:
             ru = time_default_stream(theirs)
             r.update({"reference_us": ru, "reference_GBps": nbytes / ru / 1e3, "speedup": ru / us})
         rows[name] = r
-        print(f"{tag:8s} {name:28s} b200 {us:8.2f} us {r['b200_GBps']:7.0f} GB/s ({r['b200_frac_of_hbm_peak']:.2f})"
+        print(f"{tag:8s} {name:28s} b200 {us:8.2f} us {r['b200_GBps']:7.0f} GB/s ({r['b200_frac_of_hbm_peak']:.2f} of peak, {r['b200_frac_of_copy_speed']:.2f} of a same-bytes copy at {cu:.2f} us)"
               + (f"   reference {r['reference_us']:9.2f} us   x{r['speedup']:.1f}" if "speedup" in r else ""), flush=True)
 
     row("grouping2 fwd", B * (n * c + n * k + n * k * c),

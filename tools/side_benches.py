@@ -67,7 +67,15 @@ with torch.no_grad():
         us = graph_time(run)
         n_out = len(want) + (1 if "ml_norm" in want else 0)
         nbytes = 4 * n * (K + (1 if use_conf else 0) + n_out)
-        rows.append({"n": n, "K": K, "what": what, "us": us, "alg_MB": nbytes / 1e6, "GBps": nbytes / us / 1e3, "frac_of_hbm_peak": nbytes / us / 1e3 / HBM})
+        # what a launch of this size can reach at all: a plain copy moving the same bytes, timed the same way
+        cp = [(torch.empty(nbytes // 8, device=dev), torch.empty(nbytes // 8, device=dev)) for _ in range(8)]
+
+        def run_copy():
+            i[0] += 1
+            cp[i[0] % 8][1].copy_(cp[i[0] % 8][0])
+        cu = graph_time(run_copy)
+        rows.append({"n": n, "K": K, "what": what, "us": us, "alg_MB": nbytes / 1e6, "GBps": nbytes / us / 1e3, "frac_of_hbm_peak": nbytes / us / 1e3 / HBM,
+                     "same_bytes_copy_us": cu, "frac_of_copy_speed": cu / us})
         print(rows[-1], flush=True)
     out["scoring_pass"] = rows
 
