@@ -1,9 +1,9 @@
 """Aggregate an ncu `--metrics gpu__time_duration.sum --csv` launch list by kernel name.
 python tools/launch_summary.py launches.csv [rooms]"""
-import csv, sys, re, collections
+import csv, gzip, sys, re, collections
 rooms = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 rows = []
-with open(sys.argv[1], newline="") as f:
+with (gzip.open(sys.argv[1], "rt", newline="") if sys.argv[1].endswith(".gz") else open(sys.argv[1], newline="")) as f:
     lines = [l for l in f if not l.startswith("==")]
 rdr = csv.DictReader(lines)
 agg = collections.OrderedDict()
