@@ -188,7 +188,10 @@ fps_merge_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
     // a call with scenes on both sides of the cluster capacity launches both forms; each takes its own scenes
     if (GX ? n <= cap_points : n > C * T * P) return;
 
-    const bool in_cells = scenes != nullptr && scenes[scene].use_grid;
+    // the points arrive spatially ordered with their original index in .w: either the kNN grid's cell-sorted array
+    // (cell_start != NULL: the scene starts at its first cell) or the launcher's Morton-ordered copy (cell_start == NULL:
+    // every scene sits at its own offset)
+    const bool in_cells = sorted != nullptr && (cell_start == nullptr || (scenes != nullptr && scenes[scene].use_grid));
     // SP (shared-memory points): the coordinates are read from the float4 copy in shared memory where they are used
     // instead of living in 3 * P registers -- with row pruning an update touches a few rows only, so the extra LDS.128
     // per row is noise, and at <= 128 registers a second CTA (another room's FPS cluster, or the feature path's
@@ -200,7 +203,7 @@ fps_merge_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
     // points (one per lane) of a register slot -- in cell order a patch of a few cells, far tighter than the warp's box
     float rlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, rhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     bool box_ok = true;
-    const int sbase = in_cells ? __ldg(cell_start + scenes[scene].cell_base) : 0;
+    const int sbase = !in_cells ? 0 : (cell_start ? __ldg(cell_start + scenes[scene].cell_base) : s_n);
     float4* const warp_pts = s_pts + warp * P * 32;
 #pragma unroll
     for (int p = 0; p < P; p++) {

@@ -20,8 +20,13 @@ constexpr int SCAN_TILE = 2048;        // elements per scan block (512 threads x
 
 struct GridLayout {
     int64_t cap;  // capacity of the cell arrays
-    size_t off_scene, off_bbox, off_cnt, off_start, off_tiles, off_pcell, off_sorted, total;
+    size_t off_scene, off_bbox, off_cnt, off_start, off_tiles, off_pcell, off_sorted, off_fps, fps_bytes, total;
 };
+
+// scratch of the FPS launcher inside the grid workspace (fps.cu orders the points along a Morton curve before the
+// cluster kernel reads them): ordered float4 copy | u64 keys x 2 | u32 values x 2 | radix-sort temporary
+constexpr size_t FPS_SORT_TEMP_FIXED = 1 << 20;
+static inline size_t fps_order_bytes(int64_t n) { return (size_t)n * (16 + 16 + 8 + 4) + FPS_SORT_TEMP_FIXED + 5 * 256; }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -37,6 +42,7 @@ static inline GridLayout grid_layout(int64_t n, int b, float cell_pts) {
     L.off_tiles = o;  o = align_up(o + sizeof(int) * (size_t)(L.cap / SCAN_TILE + 2), 256);
     L.off_pcell = o;  o = align_up(o + sizeof(int) * (size_t)n, 256);
     L.off_sorted = o; o = align_up(o + sizeof(float4) * (size_t)n, 256);
+    L.off_fps = o;    L.fps_bytes = fps_order_bytes(n); o = align_up(o + L.fps_bytes, 256);
     L.total = o;
     return L;
 }

@@ -12,7 +12,7 @@ from . import _common as C
 USE_GRID = os.environ.get("POINTOPS_B200_FPS_GRID", "1") != "0"
 CLUSTER_HINT = int(os.environ.get("POINTOPS_B200_FPS_CLUSTER", "0"))   # 0 = the library chooses; 1/2/4/8/16 force
 # schedule of the kernel (include/pointops_b200.h POB_FPS_*): same samples, bit for bit, whatever is chosen
-VARIANTS = {"auto": 0, "merge": 1, "chain": 2, "single": 3}
+VARIANTS = {"auto": 0, "merge": 1, "chain": 2, "single": 3, "merge_cells": 4}
 VARIANT = VARIANTS[os.environ.get("POINTOPS_B200_FPS", "auto")]
 RESIDENT_MAX = 131072   # points per scene the cluster-resident kernels hold in registers
 STATS = None            # diagnostics (bench.py): device int64[4] every launch accumulates {rounds, samples, distances, -} into

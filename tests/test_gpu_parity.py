@@ -143,7 +143,7 @@ def test_fps_full_size_80k_to_20k(cuda, oracle):
     assert torch.equal(out.cpu(), ref)
 
 
-@pytest.mark.parametrize("variant", ["merge", "chain", "single"])
+@pytest.mark.parametrize("variant", ["merge", "merge_cells", "chain", "single"])
 @pytest.mark.parametrize("sizes,stride", [([80000], 4), ([52000, 45000], 4), ([100000], 16), ([131072], 64),
                                           ([20000], 4), ([5000, 3000, 2049], 4)])
 def test_fps_variants_same_result(cuda, oracle, variant, sizes, stride):
