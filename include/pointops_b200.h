@@ -125,7 +125,7 @@ int pob_random_ball_query(int64_t m, int nsample, float min_radius, float max_ra
  * xyz / offset, with its n (rows of xyz) and cell_pts; the kernel then walks the points in cell
  * order and skips, exactly, every warp whose bounding box is out of the new sample's reach.
  * The result is bit-identical with or without it.  The MERGE variant re-orders the points along a
- * Morton curve first (~20 us; compact rows and warps prune better: -8..16 % kernel time) and keeps that
+ * Hilbert curve first (~20 us; compact rows and warps prune better: -17..19 % kernel time) and keeps that
  * copy in the workspace's own FPS region -- the workspace is written, the kNN arrays in it are not.   */
 /* variant: which schedule of the same algorithm runs (the sampled indices never depend on it):
  *   POB_FPS_AUTO   (0) the library chooses (= MERGE)
@@ -133,7 +133,7 @@ int pob_random_ball_query(int64_t m, int nsample, float min_radius, float max_ra
  *                      exchange accepts the exact global prefix (~20 samples per exchange on room-shaped clouds)
  *   POB_FPS_CHAIN  (2) round-1 kernel: one candidate + bound per CTA and exchange (~4.5 samples per exchange)
  *   POB_FPS_SINGLE (3) one sample per exchange
- *   POB_FPS_MERGE_CELLS (4) MERGE without the Morton re-ordering (points in the grid's cell order; A/B)
+ *   POB_FPS_MERGE_CELLS (4) MERGE without the Hilbert re-ordering (points in the grid's cell order; A/B)
  * stats_u64x4: NULL, or a device pointer to 4 x uint64 {rounds, samples, point distances evaluated, reserved}
  * the launch accumulates into (mean samples accepted per cluster-wide exchange = samples / rounds; the third
  * counter is filled by the MERGE variant only).  Per-call arguments: the library keeps no tuning state

@@ -853,12 +853,13 @@ static int launch_merge_grid(int P, int G, cudaStream_t stream, void** args) {
     return 0;
 }
 
-// ---- Morton order of the input (merged-list kernels) ----
+// ---- space-filling-curve order of the input (merged-list kernels) ----
 // The cluster kernel prunes by the bounding boxes of rows (32 consecutive points) and warps (P rows), so it wants
 // consecutive points to be compact blobs.  The kNN grid's cell-sorted array runs x-fastest: a warp's 640 points are a
-// strip across the room.  Sorting the points of every scene along a 30-bit Morton curve (10 bits per axis over the
-// scene's own extent) costs ~20 us and takes 8-16 % off the kernel (80 000 -> 20 000: 3.93 -> 3.48 ms; fewer rounds
-// AND fewer touched rows per sample; tools/fps_order_experiment.py).  The samples are the same whatever the order.
+// strip across the room.  Sorting the points of every scene along a 30-bit Hilbert curve (10 bits per axis over the
+// scene's own extent) costs ~20 us and takes 17-19 % off the kernel (80 000 -> 20 000: 3.94 -> 3.25 ms; fewer rounds
+// AND a third fewer touched rows per sample; tools/fps_order_experiment.py).  The samples are the same whatever the
+// order.
 __device__ __forceinline__ unsigned spread10(unsigned v) {
     v &= 0x3ffu;
     v = (v | (v << 16)) & 0x30000ffu;
@@ -868,7 +869,7 @@ __device__ __forceinline__ unsigned spread10(unsigned v) {
     return v;
 }
 
-__global__ void fps_morton_key_kernel(int64_t n, int b, const float* __restrict__ xyz, const int* __restrict__ offset,
+__global__ void fps_curve_key_kernel(int64_t n, int b, const float* __restrict__ xyz, const int* __restrict__ offset,
                                       const SceneGrid* __restrict__ scenes, unsigned long long* __restrict__ keys,
                                       unsigned* __restrict__ vals) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -882,7 +883,25 @@ __global__ void fps_morton_key_kernel(int64_t n, int b, const float* __restrict_
             unsigned c[3];
 #pragma unroll
             for (int a = 0; a < 3; a++) c[a] = q[a] >= 0.f ? (unsigned)fminf(q[a], 1023.f) : 0u;   // NaN -> 0
-            m = spread10(c[0]) | (spread10(c[1]) << 1) | (spread10(c[2]) << 2);
+            // Hilbert index of the 10-bit cell (Skilling's axes -> transpose form): unlike the plain Morton order,
+            // consecutive keys are always face neighbours, so rows and warps have no far jumps inside them
+            // (80 000 -> 20 000: 3.25 ms vs 3.51 Morton vs 3.94 cell order; 443 vs 579 vs 680 distances per sample)
+#pragma unroll 1
+            for (unsigned Q = 512u; Q > 1u; Q >>= 1) {
+                const unsigned Pm = Q - 1u;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    if (c[a] & Q) c[0] ^= Pm;   // a == 0: the exchange below is the identity
+                    else { const unsigned t = (c[0] ^ c[a]) & Pm; c[0] ^= t; c[a] ^= t; }
+                }
+            }
+            c[1] ^= c[0]; c[2] ^= c[1];
+            unsigned t = 0u;
+#pragma unroll 1
+            for (unsigned Q = 512u; Q > 1u; Q >>= 1)
+                if (c[2] & Q) t ^= Q - 1u;
+            c[0] ^= t; c[1] ^= t; c[2] ^= t;
+            m = (spread10(c[0]) << 2) | (spread10(c[1]) << 1) | spread10(c[2]);
         } else {   // scenes too small for a grid keep their order
             m = (unsigned)min((int64_t)0x3fffffff, i - (s == 0 ? 0 : offset[s - 1]));
         }
@@ -891,7 +910,7 @@ __global__ void fps_morton_key_kernel(int64_t n, int b, const float* __restrict_
     }
 }
 
-__global__ void fps_morton_gather_kernel(int64_t n, const float* __restrict__ xyz, const unsigned* __restrict__ vals,
+__global__ void fps_curve_gather_kernel(int64_t n, const float* __restrict__ xyz, const unsigned* __restrict__ vals,
                                          float4* __restrict__ ordered) {
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = vals[j];
@@ -900,7 +919,7 @@ __global__ void fps_morton_gather_kernel(int64_t n, const float* __restrict__ xy
 }
 
 // fills the ordered copy inside the grid workspace; returns it through *ordered_out
-static int fps_morton_order(int64_t n, int b, const float* xyz, const int* offset, const SceneGrid* scenes, char* region,
+static int fps_curve_order(int64_t n, int b, const float* xyz, const int* offset, const SceneGrid* scenes, char* region,
                             size_t region_bytes, const float4** ordered_out, cudaStream_t stream) {
     size_t o = 0;
     float4* ordered = (float4*)(region + o);               o = align_up(o + sizeof(float4) * (size_t)n, 256);
@@ -919,9 +938,9 @@ static int fps_morton_order(int64_t n, int b, const float* xyz, const int* offse
     cub::DoubleBuffer<unsigned> dv(v0, v1);
     POB_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, dk, dv, (int64_t)n, 0, 30 + scene_bits, stream));
     if (o + temp_bytes > region_bytes) return POB_ERR_WORKSPACE;
-    fps_morton_key_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(n, b, xyz, offset, scenes, k0, v0);
+    fps_curve_key_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(n, b, xyz, offset, scenes, k0, v0);
     POB_CHECK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, dk, dv, (int64_t)n, 0, 30 + scene_bits, stream));
-    fps_morton_gather_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(n, xyz, dv.Current(), ordered);
+    fps_curve_gather_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(n, xyz, dv.Current(), ordered);
     pob_count_launches(2);
     *ordered_out = ordered;
     POB_RETURN_LAST_ERROR();
@@ -937,7 +956,7 @@ using namespace pob;
 // exceeds the register-resident capacity (131072 points) and needs no initialisation.
 // grid_workspace: NULL, or the workspace pob_knn_grid_build filled for the same xyz/offset with
 // the same n, b, cell_pts -- enables exact spatial pruning; results are identical either way.  The launcher writes
-// its Morton-ordered copy of the points into the workspace's own FPS region (disjoint from what the kNN queries read).
+// its Hilbert-ordered copy of the points into the workspace's own FPS region (disjoint from what the kNN queries read).
 // cluster_hint: 0 = choose, else force 1/2/4/8/16 CTAs per scene.
 // variant: POB_FPS_AUTO (0) / POB_FPS_MERGE (1) / POB_FPS_CHAIN (2) / POB_FPS_SINGLE (3) / POB_FPS_MERGE_CELLS (4): same samples, different
 // schedules (A/B and fallback); stats: NULL or 2 x u64 on the device {rounds, samples} accumulated by the launch.
@@ -961,14 +980,14 @@ POB_API int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, 
         cell_start = (const int*)(ws + L.off_start);
         sorted = (const float4*)(ws + L.off_sorted);
     }
-    // the merged-list kernels read a Morton-ordered copy (built on first use, in the workspace's FPS region)
+    // the merged-list kernels read a Hilbert-ordered copy (built on first use, in the workspace's FPS region)
     const int* m_cell_start = cell_start;
     const float4* m_sorted = sorted;
     bool ordered_done = false;
     auto order_points = [&]() -> int {
         if (ordered_done || !grid_workspace || !reorder) return 0;
         const GridLayout L = grid_layout(n, b, cell_pts);
-        const int rc = fps_morton_order(n, b, xyz, offset, scenes, (char*)grid_workspace + L.off_fps, L.fps_bytes, &m_sorted, stream);
+        const int rc = fps_curve_order(n, b, xyz, offset, scenes, (char*)grid_workspace + L.off_fps, L.fps_bytes, &m_sorted, stream);
         if (rc) return rc;
         m_cell_start = nullptr;
         ordered_done = true;

@@ -189,7 +189,7 @@ fps_merge_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
     if (GX ? n <= cap_points : n > C * T * P) return;
 
     // the points arrive spatially ordered with their original index in .w: either the kNN grid's cell-sorted array
-    // (cell_start != NULL: the scene starts at its first cell) or the launcher's Morton-ordered copy (cell_start == NULL:
+    // (cell_start != NULL: the scene starts at its first cell) or the launcher's Hilbert-ordered copy (cell_start == NULL:
     // every scene sits at its own offset)
     const bool in_cells = sorted != nullptr && (cell_start == nullptr || (scenes != nullptr && scenes[scene].use_grid));
     // SP (shared-memory points): the coordinates are read from the float4 copy in shared memory where they are used

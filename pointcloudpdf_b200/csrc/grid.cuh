@@ -23,7 +23,7 @@ struct GridLayout {
     size_t off_scene, off_bbox, off_cnt, off_start, off_tiles, off_pcell, off_sorted, off_fps, fps_bytes, total;
 };
 
-// scratch of the FPS launcher inside the grid workspace (fps.cu orders the points along a Morton curve before the
+// scratch of the FPS launcher inside the grid workspace (fps.cu orders the points along a Hilbert curve before the
 // cluster kernel reads them): ordered float4 copy | u64 keys x 2 | u32 values x 2 | radix-sort temporary
 constexpr size_t FPS_SORT_TEMP_FIXED = 1 << 20;
 static inline size_t fps_order_bytes(int64_t n) { return (size_t)n * (16 + 16 + 8 + 4) + FPS_SORT_TEMP_FIXED + 5 * 256; }
