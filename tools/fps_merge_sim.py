@@ -42,6 +42,32 @@ if ORDER.startswith("morton"):
         return out
     code = spread(blk[:, 0]) | (spread(blk[:, 1]) << 1) | (spread(blk[:, 2]) << 2)
     key = code * (dd.prod() + 1) + key     # Morton over blocks, row-major (z, y, x) inside a block
+if ORDER == "hilbert":                 # what the launcher does: 10-bit Hilbert index over the scene's extent
+    ext = Lb.max()
+    c = np.minimum((xyz - xyz.min(0)) / ext * 1024.0, 1023.0).astype(np.int64)
+    X = [c[:, 0].copy(), c[:, 1].copy(), c[:, 2].copy()]
+    Q = 512
+    while Q > 1:
+        P_ = Q - 1
+        for i in range(3):
+            hit = (X[i] & Q) != 0
+            t = (X[0] ^ X[i]) & P_
+            x0 = np.where(hit, X[0] ^ P_, X[0] ^ t)
+            if i:
+                X[i] = np.where(hit, X[i], X[i] ^ t)
+            X[0] = x0 if i else np.where(hit, X[0] ^ P_, X[0])
+        Q >>= 1
+    X[1] ^= X[0]; X[2] ^= X[1]
+    t = np.zeros_like(X[0]); Q = 512
+    while Q > 1:
+        t = np.where((X[2] & Q) != 0, t ^ (Q - 1), t); Q >>= 1
+    X = [x ^ t for x in X]
+    def spread(v):
+        out = np.zeros_like(v)
+        for i in range(10):
+            out |= ((v >> i) & 1) << (3 * i)
+        return out
+    key = (spread(X[0]) << 2) | (spread(X[1]) << 1) | spread(X[2])
 order = np.argsort(key, kind="stable")
 pts = xyz[order]
 gid = order
