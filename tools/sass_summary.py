@@ -16,7 +16,7 @@ PATTERNS = [("UBLKCP", r"\bUBLKCP"), ("SYNCS (mbarrier)", r"\bSYNCS\."), ("ST.AS
             ("ATOM / RED (any)", r"\b(ATOM|ATOMG|ATOMS|RED|REDG)\b|\b(ATOM|ATOMG|ATOMS|RED|REDG)\."), ("UCGABAR (cluster barrier)", r"UCGABAR"),
             ("LDG.E.128", r"LDG\.E\.128|LDG\.E\.[A-Z.]*128"), ("STG.E.128", r"STG\.E\.128|STG\.E\.[A-Z.]*128"),
             ("LDS.128", r"LDS\.128"), ("STS.128", r"STS\.128"), ("STL/LDL (local)", r"\b(STL|LDL)\b|\b(STL|LDL)\."),
-            ("FFMA", r"\bFFMA"), ("BAR.SYNC", r"BAR\.SYNC")]
+            ("FFMA", r"\bFFMA"), ("HMMA (mma.sync tensor core)", r"\bHMMA"), ("LDGSTS (cp.async)", r"\bLDGSTS"), ("BAR.SYNC", r"BAR\.SYNC")]
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 kern, counts, total = None, collections.OrderedDict(), {}
 for line in sass.splitlines():
@@ -32,7 +32,7 @@ for line in sass.splitlines():
             if re.search(pat, line):
                 counts[kern][name] += 1
 want = sys.argv[1:] or ["fps_merge", "fps_chain", "fps_cluster", "knn_grid", "aggregation_fwd_pipe", "aggregation_bwd_fast", "gather_rows_fast<float, 8, 8",
-                        "group_xyz", "scatter_rows_fast<8", "reduce_neighbours_fast<8", "pt_layer_tile", "score_fused", "linear_tile_kernel<128"]
+                        "group_xyz", "scatter_rows_fast<8", "reduce_neighbours_fast<8", "pt_layer_tile", "score_fused", "linear_tile_kernel<128", "linear_mma_kernel", "fps_curve"]
 print("# SASS evidence per kernel (`cuobjdump -sass pointcloudpdf_b200/lib/libpointops_b200.so`, sm_100a)\n")
 print("Counts of SASS instructions by mnemonic, per kernel instantiation (static counts, not executed counts).\n")
 cols = [n for n, _ in PATTERNS]
