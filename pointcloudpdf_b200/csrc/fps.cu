@@ -853,6 +853,89 @@ static int launch_merge_grid(int P, int G, cudaStream_t stream, void** args) {
     return 0;
 }
 
+// ---- tiny scenes (<= 2 048 points): one CTA per scene, one sample per iteration, nothing speculative ----
+// For the last stage of a room (1 250 -> 312) a round of the cluster kernels (1-3 us of exchange, ranking and list
+// upkeep for 2-4 samples) costs more than the plain chain: a CTA of 8 warps keeps its scene in registers (P points per
+// thread), and an iteration is update -> 64-bit key max inside the warp (two REDUX) -> one shared-memory slot per warp ->
+// ONE __syncthreads (slots are double buffered) -> the same two REDUX over the warp slots -> winner's coordinates from the
+// shared-memory copy: ~250-300 ns (1 250 -> 312: 0.098 ms against 0.124 for the round-1 chain kernel on one CTA).  Beyond
+// ~2 000 points one SM's issue rate bounds the update (5 000 points on 1 024 threads: 860 ns per sample) and the
+// cluster kernels win again.
+// Keys are (d2 bits << 32) | (0x7fffffff - index): the maximum is the farthest point, ties to the lowest index.
+template <int T, int P>
+__global__ void __launch_bounds__(T)
+fps_small_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
+                 int* __restrict__ idx, unsigned long long* __restrict__ stats) {
+    extern __shared__ __align__(16) float4 sm_pts[];   // [T * P]
+    __shared__ unsigned long long s_best[2][32];
+    constexpr int NW = T / 32;
+    const int scene = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s_n = scene == 0 ? 0 : offset[scene - 1], n = offset[scene] - s_n;
+    const int s_m = scene == 0 ? 0 : new_offset[scene - 1], m = new_offset[scene] - s_m;
+    if (n <= 0 || m <= 0) return;
+    float px[P], py[P], pz[P], tmp[P];
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        const int i = tid + k * T;
+        px[k] = py[k] = pz[k] = 0.f;
+        tmp[k] = -1.f;                       // never a maximum
+        if (i < n) {
+            px[k] = __ldg(xyz + (int64_t)(s_n + i) * 3); py[k] = __ldg(xyz + (int64_t)(s_n + i) * 3 + 1); pz[k] = __ldg(xyz + (int64_t)(s_n + i) * 3 + 2);
+            tmp[k] = PLACEHOLDER_D2;
+            sm_pts[i] = make_float4(px[k], py[k], pz[k], 0.f);
+        }
+    }
+    if (tid < 64) s_best[tid >> 5][tid & 31] = 0ull;
+    if (tid == 0) idx[s_m] = s_n;
+    __syncthreads();
+    float4 cur = sm_pts[0];
+    for (int j = 1; j < m; j++) {
+        const int par = j & 1;
+        unsigned long long best = 0ull;
+#pragma unroll
+        for (int k = 0; k < P; k++) {
+            const float d = d2_ref(px[k], py[k], pz[k], cur.x, cur.y, cur.z);
+            tmp[k] = fminf(d, tmp[k]);
+            const unsigned long long key = tmp[k] >= 0.f ? ((unsigned long long)__float_as_uint(tmp[k]) << 32) | (unsigned)(0x7fffffff - (s_n + tid + k * T)) : 0ull;
+            best = key > best ? key : best;
+        }
+        {
+            const unsigned hi = (unsigned)(best >> 32), mh = __reduce_max_sync(FULL, hi);
+            const unsigned ml = __reduce_max_sync(FULL, hi == mh ? (unsigned)best : 0u);
+            if (lane == 0) s_best[par][warp] = ((unsigned long long)mh << 32) | ml;
+        }
+        __syncthreads();   // the slots of the other parity are rewritten only after the next barrier
+        const unsigned long long wk = lane < NW ? s_best[par][lane] : 0ull;
+        const unsigned hi = (unsigned)(wk >> 32), mh = __reduce_max_sync(FULL, hi);
+        const unsigned ml = __reduce_max_sync(FULL, hi == mh ? (unsigned)wk : 0u);
+        const int win = 0x7fffffff - (int)ml;
+        cur = sm_pts[win - s_n];
+        if (tid == 0) idx[s_m + j] = win;
+    }
+    if (stats && tid == 0) {   // one sample per round; every point meets every sample
+        atomicAdd(stats, (unsigned long long)(m - 1));
+        atomicAdd(stats + 1, (unsigned long long)(m - 1));
+        atomicAdd(stats + 2, (unsigned long long)(m - 1) * (unsigned long long)n);
+    }
+}
+
+template <int T>
+static int launch_small(int P, int b, cudaStream_t stream, const float* xyz, const int* offset, const int* new_offset, int* idx,
+                        unsigned long long* stats) {
+#define POB_FPS_CASE(PP)                                                                                                    \
+    if (P <= PP) {                                                                                                          \
+        constexpr size_t smem = sizeof(float4) * T * PP;                                                                    \
+        auto kern = fps_small_kernel<T, PP>;                                                                                \
+        if (smem > 32 * 1024) POB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<b, T, smem, stream>>>(xyz, offset, new_offset, idx, stats);                                                      \
+        pob_count_launches(1);                                                                                              \
+        POB_RETURN_LAST_ERROR();                                                                                            \
+    }
+    POB_FPS_CASE(1) POB_FPS_CASE(2) POB_FPS_CASE(3) POB_FPS_CASE(4) POB_FPS_CASE(5) POB_FPS_CASE(6) POB_FPS_CASE(8)
+#undef POB_FPS_CASE
+    return POB_ERR_UNSUPPORTED;
+}
+
 // ---- space-filling-curve order of the input (merged-list kernels) ----
 // The cluster kernel prunes by the bounding boxes of rows (32 consecutive points) and warps (P rows), so it wants
 // consecutive points to be compact blobs.  The kNN grid's cell-sorted array runs x-fastest: a warp's 640 points are a
@@ -979,6 +1062,10 @@ POB_API int pob_farthest_point_sampling(int b, int64_t n_max, const float* xyz, 
         scenes = (const SceneGrid*)(ws + L.off_scene);
         cell_start = (const int*)(ws + L.off_start);
         sorted = (const float4*)(ws + L.off_sorted);
+    }
+    const bool hinted = cluster_hint == 1 || cluster_hint == 2 || cluster_hint == 4 || cluster_hint == 8 || cluster_hint == 16;
+    if (variant == 0 && !hinted && n_max <= 2048) {   // tiny scenes: the plain one-sample-per-iteration CTA kernel is the fastest form
+        return launch_small<256>((int)ceil_div(n_max, 256), b, stream, xyz, offset, new_offset, idx, (unsigned long long*)stats_u64x4);
     }
     // the merged-list kernels read a Hilbert-ordered copy (built on first use, in the workspace's FPS region)
     const int* m_cell_start = cell_start;
