@@ -939,7 +939,7 @@ static int launch_small(int P, int b, cudaStream_t stream, const float* xyz, con
 // ---- space-filling-curve order of the input (merged-list kernels) ----
 // The cluster kernel prunes by the bounding boxes of rows (32 consecutive points) and warps (P rows), so it wants
 // consecutive points to be compact blobs.  The kNN grid's cell-sorted array runs x-fastest: a warp's 640 points are a
-// strip across the room.  Sorting the points of every scene along a 30-bit Hilbert curve (10 bits per axis over the
+// strip across the room.  Sorting the points of every scene along a 24-bit Hilbert curve (8 bits per axis over the
 // scene's own extent) costs ~20 us and takes 17-19 % off the kernel (80 000 -> 20 000: 3.94 -> 3.25 ms; fewer rounds
 // AND a third fewer touched rows per sample; tools/fps_order_experiment.py).  The samples are the same whatever the
 // order.
@@ -953,24 +953,25 @@ __device__ __forceinline__ unsigned spread10(unsigned v) {
 }
 
 __global__ void fps_curve_key_kernel(int64_t n, int b, const float* __restrict__ xyz, const int* __restrict__ offset,
-                                      const SceneGrid* __restrict__ scenes, unsigned long long* __restrict__ keys,
+                                      const SceneGrid* __restrict__ scenes, int bits, unsigned long long* __restrict__ keys,
                                       unsigned* __restrict__ vals) {
+    const float cells = (float)(1 << bits);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int s = segment_of(i, offset, b);
         const SceneGrid g = scenes[s];
         unsigned m;
         if (g.use_grid) {
             const float ext = (float)max(g.dx, max(g.dy, g.dz)) * g.h;
-            const float sc = ext > 0.f ? 1024.f / ext : 0.f;
+            const float sc = ext > 0.f ? cells / ext : 0.f;
             const float q[3] = {(__ldg(xyz + i * 3) - g.lox) * sc, (__ldg(xyz + i * 3 + 1) - g.loy) * sc, (__ldg(xyz + i * 3 + 2) - g.loz) * sc};
             unsigned c[3];
 #pragma unroll
-            for (int a = 0; a < 3; a++) c[a] = q[a] >= 0.f ? (unsigned)fminf(q[a], 1023.f) : 0u;   // NaN -> 0
-            // Hilbert index of the 10-bit cell (Skilling's axes -> transpose form): unlike the plain Morton order,
+            for (int a = 0; a < 3; a++) c[a] = q[a] >= 0.f ? (unsigned)fminf(q[a], cells - 1.f) : 0u;   // NaN -> 0
+            // Hilbert index of the cell (Skilling's axes -> transpose form): unlike the plain Morton order,
             // consecutive keys are always face neighbours, so rows and warps have no far jumps inside them
             // (80 000 -> 20 000: 3.25 ms vs 3.51 Morton vs 3.94 cell order; 443 vs 579 vs 680 distances per sample)
 #pragma unroll 1
-            for (unsigned Q = 512u; Q > 1u; Q >>= 1) {
+            for (unsigned Q = 1u << (bits - 1); Q > 1u; Q >>= 1) {
                 const unsigned Pm = Q - 1u;
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
@@ -981,14 +982,14 @@ __global__ void fps_curve_key_kernel(int64_t n, int b, const float* __restrict__
             c[1] ^= c[0]; c[2] ^= c[1];
             unsigned t = 0u;
 #pragma unroll 1
-            for (unsigned Q = 512u; Q > 1u; Q >>= 1)
+            for (unsigned Q = 1u << (bits - 1); Q > 1u; Q >>= 1)
                 if (c[2] & Q) t ^= Q - 1u;
             c[0] ^= t; c[1] ^= t; c[2] ^= t;
             m = (spread10(c[0]) << 2) | (spread10(c[1]) << 1) | spread10(c[2]);
         } else {   // scenes too small for a grid keep their order
-            m = (unsigned)min((int64_t)0x3fffffff, i - (s == 0 ? 0 : offset[s - 1]));
+            m = (unsigned)min((int64_t)((1 << (3 * bits)) - 1), i - (s == 0 ? 0 : offset[s - 1]));
         }
-        keys[i] = ((unsigned long long)s << 30) | m;
+        keys[i] = ((unsigned long long)s << (3 * bits)) | m;
         vals[i] = (unsigned)i;
     }
 }
@@ -1014,15 +1015,17 @@ static int fps_curve_order(int64_t n, int b, const float* xyz, const int* offset
     void* temp = region + o;
     size_t temp_bytes = 0;
     int scene_bits = 0;
+    // 8 bits per axis: as good as 10 (3.28 vs 3.30 ms at 80 000 points; 5 bits still is, 4 are not) and one radix pass less
+    constexpr int bits = 8;
     while ((1 << scene_bits) < b) scene_bits++;
     // double-buffer form: the sort ping-pongs between the two key / value arrays and needs only its histograms as
     // temporary storage (the plain form allocates another n keys + values there)
     cub::DoubleBuffer<unsigned long long> dk(k0, k1);
     cub::DoubleBuffer<unsigned> dv(v0, v1);
-    POB_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, dk, dv, (int64_t)n, 0, 30 + scene_bits, stream));
+    POB_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, dk, dv, (int64_t)n, 0, 3 * bits + scene_bits, stream));
     if (o + temp_bytes > region_bytes) return POB_ERR_WORKSPACE;
-    fps_curve_key_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(n, b, xyz, offset, scenes, k0, v0);
-    POB_CHECK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, dk, dv, (int64_t)n, 0, 30 + scene_bits, stream));
+    fps_curve_key_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(n, b, xyz, offset, scenes, bits, k0, v0);
+    POB_CHECK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, dk, dv, (int64_t)n, 0, 3 * bits + scene_bits, stream));
     fps_curve_gather_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(n, xyz, dv.Current(), ordered);
     pob_count_launches(2);
     *ordered_out = ordered;
