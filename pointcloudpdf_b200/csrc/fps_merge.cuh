@@ -136,6 +136,9 @@ __device__ __forceinline__ unsigned fps_row_mask(const float (&rlo)[3], const fl
 // staged in shared memory.  Ranking 740 entries by counting would cost 2 000 compares per thread, so it is
 // thresholded first: T* = the largest "first terminal" key of any CTA is where the walk must stop anyway, only
 // real entries above it (a few dozen) are compacted and ranked.
+#ifndef FPS_ONE_STEP
+#define FPS_ONE_STEP 1
+#endif
 template <int P, int T, int D, int KC, bool GX, bool SP>
 __device__ __forceinline__ void
 fps_merge_body(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset,
@@ -387,6 +390,10 @@ fps_merge_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
             } else {
                 fill = D - len;                                               // one local step per popped entry
             }
+            // at most ONE local step per warp and round: a round waits for its slowest warp, and that warp is the one
+            // refilling a void list -- the second entry follows next round (same samples per exchange in
+            // tools/fps_merge_sim.py: 18.51 vs 18.58, the slowest warp's work -21 %)
+            if (FPS_ONE_STEP && fill > 1) fill = 1;
             for (int d = 0; d < fill; d++) {
                 if (stale) { fps_warp_argmax<P>(st, warp_pts, lane, nb, ni, nx, ny, nz); stale = false; }
                 if (lane == 0) ent_store(my_wl + len, make_ent(nb, ni, nx, ny, nz, gw, !(nb == 0u && len > 0)));
@@ -400,6 +407,7 @@ fps_merge_body(const float* __restrict__ xyz, const int* __restrict__ offset, co
             }
             if (fill) {
                 if (lane == 0) ent_store(my_wl + len, make_ent(nb, ni, nx, ny, nz, gw, false));   // terminal: bound on what follows
+                else if (lane > len && lane < WL) ent_store(my_wl + lane, make_ent(0u, -1, 0.f, 0.f, 0.f, -1, false));   // a shorter list than before: the slots behind the terminal are EMPTY
                 __syncwarp();
             }
             wmaxf = __uint_as_float(my_wl[0].khi);
