@@ -18,7 +18,8 @@ OUT = os.path.join(OUT_DIR, NAME + ".so")
 
 def build(force: bool = False) -> str:
     src = os.path.join(HERE, "pointops_C_shim.cpp")
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) > os.path.getmtime(src):
+    deps = [src, os.path.join(ROOT, "include", "pointops_b200.h")]   # the shim is compiled against the C header
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) > os.path.getmtime(d) for d in deps):
         return OUT
     import torch
     from torch.utils import cpp_extension as ce
