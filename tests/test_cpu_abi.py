@@ -107,3 +107,12 @@ def test_product_never_imports_the_oracle():
 def test_offset_helpers():
     from pointcloudpdf_b200.pointops import _common as C
     assert C.scene_sizes([5, 12, 12, 20]) == [5, 7, 0, 8]
+
+
+def test_fps_variant_constants_match_the_header():
+    """`variant` is a per-call argument of pob_farthest_point_sampling: the python names must be the header's numbers."""
+    import re
+    from pointcloudpdf_b200.pointops import sampling
+    text = open(os.path.join(ROOT, "include", "pointops_b200.h")).read()
+    header = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r"#define\s+POB_FPS_(\w+)\s+(\d+)", text)}
+    assert header == sampling.VARIANTS, (header, sampling.VARIANTS)
