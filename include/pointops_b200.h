@@ -54,7 +54,9 @@ const char* pob_error_string(int code);
  * fma(dz,dz, fma(dx,dx, dy*dy)), what the reference binary executes.  dist receives d2
  * (take_sqrt = 0, like the reference kernel) or sqrt(d2) (take_sqrt = 1, what
  * functions/query.py:24 hands to callers); may be NULL.  nsample <= 256.
- * Extra arguments vs the reference: n (rows of xyz) and b (scenes) size the search grid.      */
+ * Extra arguments vs the reference: n (rows of xyz) and b (scenes) size the search grid.
+ * The workspace (about 70 n bytes + 1 MB) also holds the scratch region pob_farthest_point_sampling uses when it
+ * is handed this grid (its curve-ordered copy of the points and the radix-sort buffers).      */
 size_t pob_knn_grid_workspace_bytes(int64_t n, int b, float cell_pts);
 int pob_knn_grid_build(int64_t n, int b, const float* xyz, const int* offset, float cell_pts,
                        void* workspace, size_t workspace_bytes, cudaStream_t stream);
